@@ -1,0 +1,262 @@
+// C ABI of libddm_b200.so (declared in include/ddm_b200.h).  Host-side only: argument validation, TMA descriptor
+// encoding and kernel launches on the caller's stream.  No allocation, no synchronisation, no CPU fallback.
+#include "../../include/ddm_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <cstring>
+
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int g_num_sms = 0;
+bool g_ready = false;
+std::atomic<long long> g_launches{0};
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int finish(int launches) {
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    return static_cast<int>(cudaPeekAtLastError());
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+// bf16 tensor map, 128-byte swizzle, zero fill out of bounds.  dims/strides innermost first; strides in elements.
+int encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims,
+                    const unsigned long long* strides_elems, const unsigned* box) {
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+    for (int i = 1; i < rank; ++i) {
+        gstr[i - 1] = strides_elems[i] * 2ull;
+        if (gstr[i - 1] % 16ull != 0) return DDM_E_ALIGNMENT;
+    }
+    if (!aligned16(base)) return DDM_E_ALIGNMENT;
+    const CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                                gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : DDM_E_DRIVER;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddm_abi_version(void) { return DDM_ABI_VERSION; }
+
+long long ddm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* ddm_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case DDM_E_NOT_INITIALISED: return "ddm_init has not been called (or failed)";
+        case DDM_E_BAD_ARGUMENT: return "bad argument";
+        case DDM_E_UNSUPPORTED: return "unsupported shape or option";
+        case DDM_E_ALIGNMENT: return "pointer or stride not 16-byte aligned";
+        case DDM_E_DRIVER: return "CUDA driver call failed (cuTensorMapEncodeTiled / entry point)";
+        case DDM_E_WRONG_ARCH: return "device is not compute capability 10.x (B200, sm_100a)";
+        default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown ddm error";
+    }
+}
+
+int ddm_init(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (prop.major != 10) return DDM_E_WRONG_ARCH;
+    g_num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) return DDM_E_DRIVER;
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    int r = ddm::conv_prepare_attributes();
+    if (r != 0) return r;
+    r = ddm::stem_prepare_attributes();
+    if (r != 0) return r;
+    g_ready = true;
+    return 0;
+}
+
+int ddm_conv2d(const ddm_conv_args* a, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (a == nullptr || a->src0 == nullptr || a->weight == nullptr || a->out == nullptr) return DDM_E_BAD_ARGUMENT;
+    if (a->ntaps < 1 || a->ntaps > DDM_MAX_TAPS || a->B < 1 || a->H < 1 || a->W < 1 || a->N < 1) return DDM_E_BAD_ARGUMENT;
+    if (a->C0 < 8 || (a->C0 % 8) != 0 || (a->src1 != nullptr && (a->C1 < 8 || (a->C1 % 8) != 0))) return DDM_E_UNSUPPORTED;
+    if ((a->ld0 % 8) != 0 || (a->src1 != nullptr && (a->ld1 % 8) != 0)) return DDM_E_ALIGNMENT;
+    if (a->view != 0 && a->view != 1) return DDM_E_BAD_ARGUMENT;
+    if (a->view == 1 && a->src1 != nullptr) return DDM_E_UNSUPPORTED;
+    if ((a->N_pad % 16) != 0 || a->N_pad < a->N || (a->K_pad % 64) != 0) return DDM_E_BAD_ARGUMENT;
+    if (!a->out_f32_nchw && ((a->ld_out % 8) != 0 || !aligned16(a->out))) return DDM_E_ALIGNMENT;
+    if (a->residual != nullptr && ((a->ld_res % 8) != 0 || !aligned16(a->residual))) return DDM_E_ALIGNMENT;
+
+    ddm::ConvParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.B = a->B; p.H = a->H; p.W = a->W;
+    // tile box: 128 pixels = bw x bh x bb (powers of two), x fastest
+    p.bw = a->W >= 128 ? 128 : pow2_ceil(a->W);
+    p.bh = pow2_ceil(a->H); if (p.bh > 128 / p.bw) p.bh = 128 / p.bw;
+    p.bb = 128 / (p.bw * p.bh);
+    p.tiles_x = (a->W + p.bw - 1) / p.bw;
+    p.tiles_y = (a->H + p.bh - 1) / p.bh;
+    const int tiles_b = (a->B + p.bb - 1) / p.bb;
+    p.m_tiles = p.tiles_x * p.tiles_y * tiles_b;
+    p.n_tiles = (a->N_pad + 255) / 256;
+    p.block_n = ((a->N_pad + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;   // e.g. N=384 -> 2 tiles of 192
+    p.total_tiles = p.m_tiles * p.n_tiles;
+    p.N = a->N;
+    if (a->norm_g != nullptr && p.n_tiles != 1) return DDM_E_UNSUPPORTED;
+    if (a->rnorm_out != nullptr && (p.n_tiles != 1 || a->out_f32_nchw)) return DDM_E_UNSUPPORTED;
+    p.ntaps = a->ntaps;
+    for (int t = 0; t < a->ntaps; ++t) { p.tap_dy[t] = a->tap_dy[t]; p.tap_dx[t] = a->tap_dx[t]; p.tap_p[t] = a->tap_p[t]; }
+    const int ceff0 = a->view == 1 ? 2 * a->C0 : a->C0;
+    p.chunks0 = (ceff0 + 63) / 64;
+    p.chunks1 = a->src1 != nullptr ? (a->C1 + 63) / 64 : 0;
+    if (a->ntaps * (p.chunks0 + p.chunks1) * 64 != a->K_pad) return DDM_E_BAD_ARGUMENT;
+    p.tmem_cols = pow2_ceil(2 * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
+    p.acc_stride = p.tmem_cols / 2;
+    const int stage_bytes = ddm::kATileBytes + p.block_n * 128;
+    p.num_stages = (200 * 1024) / stage_bytes; if (p.num_stages > 8) p.num_stages = 8;
+    p.bias = a->bias; p.row_scale = a->row_scale; p.norm_g = a->norm_g; p.scale_shift = a->scale_shift;
+    p.ss_stride = a->ss_stride; p.act = a->act;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ld_res = a->ld_res;
+    p.out = a->out; p.out_f32_nchw = a->out_f32_nchw; p.ld_out = a->ld_out;
+    p.OH = a->OH; p.OW = a->OW; p.oy = a->oy; p.ox = a->ox; p.sy = a->sy; p.sx = a->sx;
+    p.rnorm_out = a->rnorm_out;
+
+    CUtensorMap tmA0, tmA1, tmW;
+    const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};
+    auto encode_src = [&](CUtensorMap* tm, const void* base, int C, int ld) -> int {
+        unsigned long long dims[5], str[5];
+        const unsigned long long W = a->W, H = a->H, B = a->B, L = ld;
+        if (a->view == 0) {           // [B,H,W,C] -> (c, x, p=1, y, b)
+            dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B;
+            str[0] = 1; str[1] = L; str[2] = L * W; str[3] = L * W; str[4] = L * W * H;
+        } else {                      // [B,2H,2W,C] -> ((p2 c), x, p1, y, b); requires ld == C
+            if (ld != C) return DDM_E_UNSUPPORTED;
+            dims[0] = 2ull * C; dims[1] = W; dims[2] = 2; dims[3] = H; dims[4] = B;
+            str[0] = 1; str[1] = 2ull * L; str[2] = 2ull * W * L; str[3] = 4ull * W * L; str[4] = 4ull * W * H * L;
+        }
+        return encode_bf16_map(tm, base, 5, dims, str, box);
+    };
+    int r = encode_src(&tmA0, a->src0, a->C0, a->ld0);
+    if (r != 0) return r;
+    if (a->src1 != nullptr) {
+        r = encode_src(&tmA1, a->src1, a->C1, a->ld1);
+        if (r != 0) return r;
+    } else {
+        tmA1 = tmA0;
+    }
+    {
+        const unsigned long long dims[2] = {static_cast<unsigned long long>(a->K_pad), static_cast<unsigned long long>(a->N_pad)};
+        const unsigned long long str[2] = {1ull, static_cast<unsigned long long>(a->K_pad)};
+        const unsigned wbox[2] = {64u, static_cast<unsigned>(p.block_n)};
+        r = encode_bf16_map(&tmW, a->weight, 2, dims, str, wbox);
+        if (r != 0) return r;
+    }
+    ddm::launch_conv(tmA0, tmA1, tmW, p, g_num_sms, as_stream(stream));
+    return finish(1);
+}
+
+int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* weight,
+                  const float* bias, void* out_bf16, int B, int H, int W, int Cout, int ksize, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (in0 == nullptr || weight == nullptr || bias == nullptr || out_bf16 == nullptr || (ksize % 2) != 1) return DDM_E_BAD_ARGUMENT;
+    if (ddm::stem_smem_bytes(c0 + c1 + c2, Cout, ksize) > 200 * 1024 || B > 65535) return DDM_E_UNSUPPORTED;
+    if ((Cout % 8) != 0 || !aligned16(out_bf16)) return DDM_E_ALIGNMENT;
+    ddm::launch_stem(in0, c0, in1, c1, in2, c2, weight, bias, out_bf16, B, H, W, Cout, ksize, as_stream(stream));
+    return finish(1);
+}
+
+int ddm_sinusoidal_embedding(const float* t, float* out, int rows, int dim, float theta, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (dim < 4 || (dim % 2) != 0 || rows < 1) return DDM_E_BAD_ARGUMENT;
+    ddm::launch_sinusoidal(t, out, rows, dim, theta, as_stream(stream));
+    return finish(1);
+}
+
+int ddm_small_linear(const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int rows, int N, int K,
+                     int act_in, int act_out, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (rows < 1 || N < 1 || K < 1) return DDM_E_BAD_ARGUMENT;
+    ddm::launch_small_linear(x, ldx, W, b, y, ldy, rows, N, K, act_in, act_out, as_stream(stream));
+    return finish(1);
+}
+
+int ddm_row_rnorm(const void* x_bf16, int ld, float* rnorm, long long rows, int C, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if ((C % 8) != 0 || (ld % 8) != 0 || !aligned16(x_bf16)) return DDM_E_ALIGNMENT;
+    ddm::launch_row_rnorm(x_bf16, ld, rnorm, rows, C, as_stream(stream));
+    return finish(1);
+}
+
+int ddm_rmsnorm_act(const void* x_bf16, const float* norm_g, const float* scale_shift, long long ss_stride,
+                    long long rows_per_batch, int act, const void* residual_bf16, void* out_bf16, long long rows, int C,
+                    void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if ((C % 8) != 0 || !aligned16(x_bf16) || !aligned16(out_bf16) || (residual_bf16 != nullptr && !aligned16(residual_bf16)))
+        return DDM_E_ALIGNMENT;
+    if (rows_per_batch < 1) return DDM_E_BAD_ARGUMENT;
+    ddm::launch_rmsnorm_act(x_bf16, norm_g, scale_shift, ss_stride, rows_per_batch, act, residual_bf16, out_bf16, rows, C,
+                            as_stream(stream));
+    return finish(1);
+}
+
+int ddm_linear_attention(const void* qkv_bf16, const float* mem_kv, void* out_bf16, int B, int n, int heads, int d,
+                         int n_mem, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (!aligned16(qkv_bf16) || !aligned16(out_bf16)) return DDM_E_ALIGNMENT;
+    if (B > 65535 || n_mem < 0 || n_mem > 16 || (n_mem > 0 && mem_kv == nullptr)) return DDM_E_UNSUPPORTED;
+    const int r = ddm::launch_linear_attention(qkv_bf16, mem_kv, out_bf16, B, n, heads, d, n_mem, as_stream(stream));
+    return r != 0 ? r : finish(1);
+}
+
+int ddm_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const float* mem_k,
+                  const float* mem_v, int n_mem, void* out_bf16, int B, int nq, int nk, int heads, int d, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out_bf16) || (ldq % 8) || (ldk % 8) || (ldv % 8))
+        return DDM_E_ALIGNMENT;
+    if (B > 65535 || heads > 65535 || n_mem < 0 || n_mem > 64) return DDM_E_UNSUPPORTED;
+    const int r = ddm::launch_attention(q, ldq, k, ldk, v, ldv, mem_k, mem_v, n_mem, out_bf16, B, nq, nk, heads, d, as_stream(stream));
+    return r != 0 ? r : finish(1);
+}
+
+int ddm_sampler_step(int kind, float* x, const float* model_out, const float* noise, long long noise_step_stride,
+                     float* x_start_out, const float* coef,
+                     int* step_counter, int advance, int objective, unsigned long long seed, long long numel, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if ((kind != DDM_SAMPLER_DDIM && kind != DDM_SAMPLER_DDPM) || objective < 0 || objective > 2 || numel < 1) return DDM_E_BAD_ARGUMENT;
+    ddm::launch_sampler_step(kind, x, model_out, noise, noise_step_stride, x_start_out, coef, step_counter, advance, objective, seed, numel,
+                             as_stream(stream));
+    return finish(advance ? 2 : 1);
+}
+
+int ddm_finalize(const float* x, float* y, int unnormalize, long long numel, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    ddm::launch_finalize(x, y, unnormalize, numel, as_stream(stream));
+    return finish(1);
+}
+
+int ddm_select_row(const float* table, const int* step_counter, float* dst, int row_len, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    ddm::launch_select_row(table, step_counter, dst, row_len, as_stream(stream));
+    return finish(1);
+}
+
+int ddm_randn(float* x, unsigned long long seed, unsigned long long stream_id, long long numel, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    ddm::launch_randn(x, seed, stream_id, numel, as_stream(stream));
+    return finish(1);
+}
+
+}  // extern "C"

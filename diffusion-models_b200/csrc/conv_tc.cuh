@@ -1,0 +1,62 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), fed by TMA, with the block epilogue fused.
+//
+// GEMM view:  M = output pixels (tiles of 128 = bw x bh x bb box of the NHWC grid), N = C_out, K = taps x C_in.
+//   A tile (128 pixels x 64 channels, bf16) : one 5-D TMA box load per (tap, 64-channel chunk); the tap offset is
+//     added to the box coordinate, and out-of-bounds pixels are zero-filled by TMA, which *is* the conv padding.
+//   B tile (block_n x 64, bf16)             : 2-D TMA box of the packed weight matrix [N_pad][K_pad] (K contiguous).
+//   D (128 x block_n fp32)                  : TMEM accumulator, double buffered so the epilogue of tile i overlaps
+//     the main loop of tile i+1.
+// Warp roles: warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner, warps 2..5 = epilogue
+// (one thread per accumulator row == one output pixel, so the per-pixel RMSNorm over C_out is thread-local).
+//
+// Reference ops folded here (denoising_diffusion.py): Block.forward :113-122 (conv -> RMSNorm -> scale/shift -> SiLU),
+// ResnetBlock residual add :148, Downsample :54-58 (view 1), Upsample :48-52 (4 sub-pixel phases, strided output),
+// skip torch.cat :378-387 (two sources), attention pre-norm :176/:218 (row_scale), to_out + RMSNorm :169-172.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace ddm {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                       // bf16 elements per k-chunk = one 128-byte swizzle row
+constexpr int kATileBytes = kTileM * kChunkK * 2; // 16 KiB
+constexpr int kMaxTaps = 9;
+constexpr int kConvThreads = 192;
+
+struct ConvParams {
+    // tile domain (pixel grid the taps are applied on) and tile box
+    int B, H, W;
+    int bw, bh, bb;
+    int tiles_x, tiles_y, m_tiles, n_tiles, total_tiles;
+    int block_n;                 // UMMA N: multiple of 16, <= 256
+    int N;                       // real C_out
+    int ntaps;
+    int tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_p[kMaxTaps];
+    int chunks0, chunks1;        // 64-channel chunks per tap for source 0 / source 1
+    int acc_stride;              // TMEM columns between the two accumulator stages
+    int tmem_cols;               // allocated TMEM columns (power of two >= 32)
+    int num_stages;              // smem ring depth
+    // epilogue
+    const float* bias;           // [N] or null
+    const float* row_scale;      // [B*H*W] or null : v = acc * row_scale[pixel]
+    const float* norm_g;         // [N] = g * sqrt(N), or null : RMSNorm over N (needs n_tiles == 1)
+    const float* scale_shift;    // [Bt][2N] (scale | shift) or null
+    long long ss_stride;         // elements between batch rows of scale_shift (0 = one shared row)
+    int act;                     // 0 none, 1 SiLU
+    const __nv_bfloat16* residual;  // added after the activation, indexed like `out`
+    int ld_res;
+    void* out;
+    int out_f32_nchw;            // 0: bf16 [B,OH,OW,ld_out] ; 1: fp32 [B,N,OH,OW]
+    int ld_out;
+    int OH, OW, oy, ox, sy, sx;  // output pixel of tile pixel (b,y,x) is (b, y*sy+oy, x*sx+ox)
+    float* rnorm_out;            // [B*OH*OW] or null : 1/max(||out_row||_2, 1e-12) of the stored row
+};
+
+void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const ConvParams& p,
+                 int num_sms, cudaStream_t stream);
+int conv_smem_bytes(int block_n, int num_stages);
+int conv_prepare_attributes();
+
+}  // namespace ddm

@@ -1,0 +1,384 @@
+// Memory-bound kernels around the tensor-core convolutions: stem conv, time-conditioning MLPs, row norms,
+// the fused per-timestep sampler update and a Philox N(0,1) generator.  All are HBM/L2-bound; the rules that
+// matter are coalescing, 16-byte vector access and enough CTAs to cover 148 SMs.
+#include "kernels.cuh"
+
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace ddm {
+
+namespace {
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return v / (1.0f + expf(-v));                               // SiLU
+    if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));   // exact-erf GELU
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ stem conv
+// One CTA = 8 x 32 output pixels of one image, one thread per pixel, 16 output channels at a time.
+constexpr int kStemTH = 8, kStemTW = 32;
+
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ in0, int c0, const float* __restrict__ in1, int c1,
+                 const float* __restrict__ in2, int c2, const float* __restrict__ weight,
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int Cout,
+                 int ks) {
+    extern __shared__ float stem_smem[];
+    const int Cin = c0 + c1 + c2;
+    const int pad = ks / 2;
+    const int PH = kStemTH + ks - 1, PW = kStemTW + ks - 1;
+    float* w_s = stem_smem;                        // [ks*ks*Cin][Cout]
+    float* patch = w_s + ks * ks * Cin * Cout;     // [Cin][PH][PW]
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * kStemTH, x0 = blockIdx.x * kStemTW;
+    for (int i = threadIdx.x; i < ks * ks * Cin * Cout; i += blockDim.x) w_s[i] = __ldg(weight + i);
+    for (int i = threadIdx.x; i < Cin * PH * PW; i += blockDim.x) {
+        const int ci = i / (PH * PW);
+        const int rem = i - ci * PH * PW;
+        const int py = rem / PW, px = rem - py * PW;
+        const int y = y0 + py - pad, x = x0 + px - pad;
+        float v = 0.0f;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const float* src;
+            int c, cn;
+            if (ci < c0) { src = in0; c = ci; cn = c0; }
+            else if (ci < c0 + c1) { src = in1; c = ci - c0; cn = c1; }
+            else { src = in2; c = ci - c0 - c1; cn = c2; }
+            v = __ldg(src + ((static_cast<long long>(b) * cn + c) * H + y) * W + x);
+        }
+        patch[i] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / kStemTW, tx = threadIdx.x % kStemTW;
+    const int y = y0 + ty, x = x0 + tx;
+    const bool valid = (y < H) && (x < W);
+    for (int cb = 0; cb < Cout; cb += 16) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = (cb + j < Cout) ? __ldg(bias + cb + j) : 0.0f;
+        // weight rows are tap-major: k = (ky*ks + kx)*Cin + ci
+        for (int ky = 0; ky < ks; ++ky) {
+            for (int kx = 0; kx < ks; ++kx) {
+                for (int ci = 0; ci < Cin; ++ci) {
+                    const float v = patch[(ci * PH + ty + ky) * PW + tx + kx];
+                    const float* wr = w_s + ((ky * ks + kx) * Cin + ci) * Cout + cb;
+                    if (cb + 16 <= Cout) {
+                        const float4* w4 = reinterpret_cast<const float4*>(wr);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 w = w4[j];
+                            acc[4 * j + 0] = fmaf(v, w.x, acc[4 * j + 0]);
+                            acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
+                            acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
+                            acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+                        }
+                    } else {
+                        for (int j = 0; j < 16 && cb + j < Cout; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+                    }
+                }
+            }
+        }
+        if (valid) {
+            __nv_bfloat16* o = out + ((static_cast<long long>(b) * H + y) * W + x) * Cout + cb;
+            if (cb + 16 <= Cout && (Cout % 8) == 0) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(acc[2 * j], acc[2 * j + 1]);
+                reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+                for (int j = 0; j < 16 && cb + j < Cout; ++j) o[j] = __float2bfloat16_rn(acc[j]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ time path
+__global__ void sinusoidal_kernel(const float* __restrict__ t, float* __restrict__ out, int rows, int dim, float theta) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * half) return;
+    const int r = i / half, j = i - r * half;
+    const float step = logf(theta) / static_cast<float>(half - 1);
+    const float f = expf(static_cast<float>(j) * -step);
+    const float a = t[r] * f;
+    out[r * dim + j] = sinf(a);
+    out[r * dim + half + j] = cosf(a);
+}
+
+// one warp per output element (r, n); lanes stride over K (coalesced reads of W rows)
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ b,
+                    float* __restrict__ y, int ldy, int rows, int N, int K, int act_in, int act_out) {
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= static_cast<long long>(rows) * N) return;
+    const int r = static_cast<int>(warp / N), n = static_cast<int>(warp - static_cast<long long>(r) * N);
+    const float* xr = x + static_cast<long long>(r) * ldx;
+    const float* wr = W + static_cast<long long>(n) * K;
+    float acc = 0.0f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(apply_act(xr[k], act_in), __ldg(wr + k), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[static_cast<long long>(r) * ldy + n] = apply_act(acc + (b != nullptr ? b[n] : 0.0f), act_out);
+}
+
+// ------------------------------------------------------------------------------------------------ row norms
+// A row of C bf16 channels is covered by `lpr` lanes (power of two <= 32), 8 channels (16 B) per lane per pass.
+__device__ __forceinline__ int lanes_per_row(int C) {
+    int l = 1;
+    while (l < 32 && l * 8 < C) l <<= 1;
+    return l;
+}
+
+__global__ void __launch_bounds__(256)
+row_rnorm_kernel(const __nv_bfloat16* __restrict__ x, int ld, float* __restrict__ rnorm, long long rows, int C) {
+    const int lpr = lanes_per_row(C);
+    const int rows_per_warp = 32 / lpr;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long row = warp * rows_per_warp + lane / lpr;
+    const int sub = lane % lpr;
+    float s = 0.0f;
+    if (row < rows) {
+        const __nv_bfloat16* xr = x + row * ld;
+        for (int c = sub * 8; c < C; c += lpr * 8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + c));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = bf16_lo(w[j]), b2 = bf16_hi(w[j]);
+                s = fmaf(a, a, fmaf(b2, b2, s));
+            }
+        }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (row < rows && sub == 0) rnorm[row] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+}
+
+__global__ void __launch_bounds__(256)
+rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g, const float* __restrict__ ss,
+                   long long ss_stride, long long rows_per_batch, int act, const __nv_bfloat16* __restrict__ res,
+                   __nv_bfloat16* __restrict__ out, long long rows, int C) {
+    const int lpr = lanes_per_row(C);
+    const int rows_per_warp = 32 / lpr;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long row = warp * rows_per_warp + lane / lpr;
+    const int sub = lane % lpr;
+    const bool live = row < rows;
+    const __nv_bfloat16* xr = x + (live ? row : 0) * C;
+    float s = 0.0f;
+    if (live) {
+        for (int c = sub * 8; c < C; c += lpr * 8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + c));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = bf16_lo(w[j]), b2 = bf16_hi(w[j]);
+                s = fmaf(a, a, fmaf(b2, b2, s));
+            }
+        }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (!live) return;
+    const float rinv = (g != nullptr) ? 1.0f / fmaxf(sqrtf(s), 1e-12f) : 1.0f;
+    const float* ssr = (ss != nullptr) ? ss + (row / rows_per_batch) * ss_stride : nullptr;
+    for (int c = sub * 8; c < C; c += lpr * 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + c));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { f[2 * j] = bf16_lo(w[j]); f[2 * j + 1] = bf16_hi(w[j]); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = f[j];
+            if (g != nullptr) t = t * rinv * __ldg(g + c + j);
+            if (ssr != nullptr) t = fmaf(t, __ldg(ssr + c + j) + 1.0f, __ldg(ssr + C + c + j));
+            if (act == 1) t = __fdividef(t, 1.0f + __expf(-t));
+            f[j] = t;
+        }
+        if (res != nullptr) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + row * C + c));
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(rw[j]); f[2 * j + 1] += bf16_hi(rw[j]); }
+        }
+        *reinterpret_cast<uint4*>(out + row * C + c) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ Philox N(0,1)
+struct Philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return {c0, c1, c2, c3};
+}
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    const float u = (static_cast<float>(a) + 0.5f) * 2.3283064365386963e-10f;   // (0,1)
+    const float v = (static_cast<float>(b) + 0.5f) * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * logf(u));
+    float s, c;
+    sincospif(2.0f * v, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+// four N(0,1) values for the element group `grp` (= element index / 4) of stream (seed, sid)
+__device__ __forceinline__ void normal4(unsigned long long seed, unsigned long long sid, unsigned long long grp, float (&z)[4]) {
+    const Philox4 p = philox4x32_10(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32), static_cast<uint32_t>(sid),
+                                    static_cast<uint32_t>(sid >> 32), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    box_muller(p.x, p.y, z[0], z[1]);
+    box_muller(p.z, p.w, z[2], z[3]);
+}
+
+__global__ void __launch_bounds__(256)
+randn_kernel(float* __restrict__ x, unsigned long long seed, unsigned long long sid, long long numel) {
+    const long long grp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i = grp * 4;
+    if (i >= numel) return;
+    float z[4];
+    normal4(seed, sid, static_cast<unsigned long long>(grp), z);
+    for (int j = 0; j < 4 && i + j < numel; ++j) x[i + j] = z[j];
+}
+
+// ------------------------------------------------------------------------------------------------ sampler step
+// Separate mul/sub/div roundings (no FMA contraction) so that the fp32 update matches the reference's chain of
+// elementwise ATen ops bit for bit (denoising_diffusion.py:570-580, 596-601, 699-701).
+__device__ __forceinline__ float clamp1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
+
+__global__ void __launch_bounds__(256)
+sampler_step_kernel(int kind, float* __restrict__ x, const float* __restrict__ mo, const float* __restrict__ noise_base,
+                    long long noise_stride, float* __restrict__ x0_out, const float* __restrict__ coef_tab, int* __restrict__ step_counter,
+                    int objective, unsigned long long seed, long long numel) {
+    const int step = *step_counter;
+    const float* noise = noise_base != nullptr ? noise_base + static_cast<long long>(step) * noise_stride : nullptr;
+    const float* cf = coef_tab + static_cast<long long>(step) * 8;
+    const float ra = cf[0], rm1 = cf[1], k2 = cf[2], k3 = cf[3], k4 = cf[4], k5 = cf[5], sac = cf[6], s1m = cf[7];
+    const long long grp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i0 = grp * 4;
+    if (i0 >= numel) return;
+    const float noise_amp = k4;                       // sigma (DDIM) or exp(0.5 logvar) (DDPM; 0 at t == 0)
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noise_amp != 0.0f && noise == nullptr) normal4(seed, static_cast<unsigned long long>(step) + 1ull, static_cast<unsigned long long>(grp), z);
+    for (int j = 0; j < 4 && i0 + j < numel; ++j) {
+        const long long i = i0 + j;
+        const float xt = x[i], o = mo[i];
+        const float rax = __fmul_rn(ra, xt);
+        float x0, eps;
+        if (objective == 0) {
+            x0 = clamp1(__fsub_rn(rax, __fmul_rn(rm1, o)));
+            eps = (kind == DDM_KIND_DDIM) ? __fdiv_rn(__fsub_rn(rax, x0), rm1) : o;
+        } else {
+            x0 = (objective == 1) ? clamp1(o) : clamp1(__fsub_rn(__fmul_rn(sac, xt), __fmul_rn(s1m, o)));
+            eps = __fdiv_rn(__fsub_rn(rax, x0), rm1);
+        }
+        const float zi = (noise != nullptr && noise_amp != 0.0f) ? noise[i] : z[j];
+        float xn;
+        if (kind == DDM_KIND_DDIM) {
+            if (k5 != 0.0f) {
+                xn = x0;                                                                  // t_next < 0 (dd:686-689)
+            } else {
+                xn = __fadd_rn(__fmul_rn(x0, k2), __fmul_rn(k3, eps));                      // x0*sqrt(a_next) + c*eps
+                if (noise_amp != 0.0f) xn = __fadd_rn(xn, __fmul_rn(noise_amp, zi));      // + sigma*noise
+            }
+        } else {
+            xn = __fadd_rn(__fmul_rn(k2, x0), __fmul_rn(k3, xt));                           // posterior mean (dd:596-598)
+            if (noise_amp != 0.0f) xn = __fadd_rn(xn, __fmul_rn(noise_amp, zi));          // dd:644
+        }
+        x[i] = xn;
+        if (x0_out != nullptr) x0_out[i] = x0;
+    }
+}
+
+__global__ void bump_counter_kernel(int* c) { *c += 1; }
+
+__global__ void __launch_bounds__(256)
+finalize_kernel(const float* __restrict__ x, float* __restrict__ y, int unnorm, long long numel) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    const float v = x[i];
+    y[i] = unnorm ? __fmul_rn(__fadd_rn(v, 1.0f), 0.5f) : v;
+}
+
+__global__ void __launch_bounds__(256)
+select_row_kernel(const float* __restrict__ table, const int* __restrict__ step_counter, float* __restrict__ dst, int row_len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < row_len) dst[i] = table[static_cast<long long>(*step_counter) * row_len + i];
+}
+
+inline unsigned blocks_for(long long n, int per_block) { return static_cast<unsigned>((n + per_block - 1) / per_block); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ launchers
+int stem_smem_bytes(int Cin, int Cout, int ks) {
+    return (ks * ks * Cin * Cout + Cin * (kStemTH + ks - 1) * (kStemTW + ks - 1)) * 4;
+}
+int stem_prepare_attributes() {
+    return static_cast<int>(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+void launch_stem(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* w, const float* b,
+                 void* out, int B, int H, int W, int Cout, int ks, cudaStream_t s) {
+    dim3 grid((W + kStemTW - 1) / kStemTW, (H + kStemTH - 1) / kStemTH, B);
+    stem_conv_kernel<<<grid, 256, stem_smem_bytes(c0 + c1 + c2, Cout, ks), s>>>(
+        in0, c0, in1, c1, in2, c2, w, b, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, Cout, ks);
+}
+void launch_sinusoidal(const float* t, float* out, int rows, int dim, float theta, cudaStream_t s) {
+    const int n = rows * (dim / 2);
+    sinusoidal_kernel<<<blocks_for(n, 128), 128, 0, s>>>(t, out, rows, dim, theta);
+}
+void launch_small_linear(const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int rows, int N, int K,
+                         int act_in, int act_out, cudaStream_t s) {
+    const long long warps = static_cast<long long>(rows) * N;
+    small_linear_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(x, ldx, W, b, y, ldy, rows, N, K, act_in, act_out);
+}
+void launch_row_rnorm(const void* x, int ld, float* rn, long long rows, int C, cudaStream_t s) {
+    int lpr = 1;
+    while (lpr < 32 && lpr * 8 < C) lpr <<= 1;
+    const long long warps = (rows + (32 / lpr) - 1) / (32 / lpr);
+    row_rnorm_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rn, rows, C);
+}
+void launch_rmsnorm_act(const void* x, const float* g, const float* ss, long long ss_stride, long long rows_per_batch, int act,
+                        const void* res, void* out, long long rows, int C, cudaStream_t s) {
+    int lpr = 1;
+    while (lpr < 32 && lpr * 8 < C) lpr <<= 1;
+    const long long warps = (rows + (32 / lpr) - 1) / (32 / lpr);
+    rmsnorm_act_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), g, ss, ss_stride,
+                                                          rows_per_batch, act, reinterpret_cast<const __nv_bfloat16*>(res),
+                                                          reinterpret_cast<__nv_bfloat16*>(out), rows, C);
+}
+void launch_sampler_step(int kind, float* x, const float* mo, const float* noise, long long noise_stride, float* x0_out, const float* coef, int* step_counter,
+                         int advance, int objective, unsigned long long seed, long long numel, cudaStream_t s) {
+    sampler_step_kernel<<<blocks_for((numel + 3) / 4, 256), 256, 0, s>>>(kind, x, mo, noise, noise_stride, x0_out, coef, step_counter, objective,
+                                                                          seed, numel);
+    if (advance) bump_counter_kernel<<<1, 1, 0, s>>>(step_counter);
+}
+void launch_finalize(const float* x, float* y, int unnorm, long long numel, cudaStream_t s) {
+    finalize_kernel<<<blocks_for(numel, 256), 256, 0, s>>>(x, y, unnorm, numel);
+}
+void launch_select_row(const float* table, const int* step_counter, float* dst, int row_len, cudaStream_t s) {
+    select_row_kernel<<<blocks_for(row_len, 256), 256, 0, s>>>(table, step_counter, dst, row_len);
+}
+void launch_randn(float* x, unsigned long long seed, unsigned long long sid, long long numel, cudaStream_t s) {
+    randn_kernel<<<blocks_for((numel + 3) / 4, 256), 256, 0, s>>>(x, seed, sid, numel);
+}
+
+}  // namespace ddm

@@ -1,0 +1,392 @@
+"""Kernel plan for one U-Net evaluation at a fixed (batch, height, width).
+
+`UnetEngine` turns a `UnetSpec` + fp32 master weights into (a) packed device weights and (b) a flat list of
+C-ABI launches over statically allocated channels-last bf16 activation buffers.  Running the plan is just walking
+that list on the current CUDA stream, so a whole step is capturable in a CUDA graph.  PyTorch is used for device
+memory and streams only; every launch is one of our kernels (see include/ddm_b200.h).
+
+Layer semantics follow denoising_diffusion.py:349-390 (Unet.forward) and the blocks at :98-229.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .arch import AttnSpec, ResBlockSpec, StageSpec, UnetSpec
+from .packing import PackedConv, norm_gain, pack_conv, pack_downsample, pack_linear, pack_stem, pack_upsample
+
+MAX_FUSED_NORM = 256     # one CTA owns a full output row in TMEM only up to 256 columns
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class UnetEngine:
+    def __init__(self, spec: UnetSpec, weights: Dict[str, torch.Tensor], batch: int, height: int, width: int,
+                 device: torch.device, time_rows: int = 1, text_tokens: int = 0, fuse_rnorm: bool = True, lib=None):
+        """`time_rows` is 1 when every sample shares the timestep (sampling loops, dd:641,682) or `batch`."""
+        assert height % spec.downsample_factor == 0 and width % spec.downsample_factor == 0, \
+            f"your input dimensions {(height, width)} need to be divisible by {spec.downsample_factor}, given the unet"
+        assert time_rows in (1, batch)
+        self.spec, self.B, self.H, self.W = spec, batch, height, width
+        self.device = torch.device(device)
+        # `lib` is a test seam (tests/fake_lib.py executes a plan with torch ops to check the host logic on CPU);
+        # the product always binds the real shared library and needs a B200.
+        if lib is not None:
+            self.lib = lib
+        else:
+            if self.device.type != "cuda":
+                raise RuntimeError("UnetEngine needs a CUDA (B200) device: there is no CPU fallback")
+            self.lib = _lib.init(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self.time_rows = time_rows
+        self.text_tokens = text_tokens
+        self.fuse_rnorm = fuse_rnorm
+        self._keep: List[object] = []            # device tensors / ctypes structs referenced by raw pointer
+        self.ops: List[Tuple[str, Callable[[int], int]]] = []
+        self.time_ops: List[Tuple[str, Callable[[int], int]]] = []
+        self.text_ops: List[Tuple[str, Callable[[int], int]]] = []
+        self.taps: Dict[str, torch.Tensor] = {}  # named activations for per-layer parity tests
+        self._w = {k: v.detach() for k, v in weights.items()}
+        self._build()
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
+        t = t.to(device=self.device, dtype=dtype or t.dtype).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _f32(self, name: str) -> torch.Tensor:
+        return self._dev(self._w[name].float().reshape(-1))
+
+    def _act(self, b: int, h: int, w: int, c: int, tag: Optional[str] = None) -> torch.Tensor:
+        t = torch.empty((b, h, w, c), dtype=torch.bfloat16, device=self.device)
+        self._keep.append(t)
+        if tag:
+            self.taps[tag] = t
+        return t
+
+    def _conv(self, tag: str, pk: PackedConv, srcs: List[torch.Tensor], out: torch.Tensor, *, domain: Tuple[int, int, int],
+              bias=None, row_scale=None, norm_g=None, ss=None, ss_stride=0, act=0, residual=None, out_f32_nchw=False,
+              out_map=(1, 1, 0, 0), rnorm_out=None, ld_src: Optional[List[int]] = None, into=None):
+        wdev = self._dev(pk.weight)
+        a = _lib.ConvArgs()
+        a.src0 = srcs[0].data_ptr()
+        a.src1 = srcs[1].data_ptr() if len(srcs) > 1 else None
+        a.C0 = pk.seg_channels[0] // (2 if pk.view == 1 else 1)
+        a.C1 = pk.seg_channels[1] if len(srcs) > 1 else 0
+        lds = ld_src or [s.shape[-1] for s in srcs]
+        a.ld0 = lds[0]
+        a.ld1 = lds[1] if len(srcs) > 1 else 0
+        a.view = pk.view
+        a.B, a.H, a.W = domain
+        a.ntaps = len(pk.taps)
+        for i, (dy, dx, p) in enumerate(pk.taps):
+            a.tap_dy[i], a.tap_dx[i], a.tap_p[i] = dy, dx, p
+        a.weight = wdev.data_ptr()
+        a.N, a.N_pad, a.K_pad = pk.n, pk.n_pad, pk.k_pad
+        a.row_scale, a.bias, a.norm_g, a.scale_shift = _ptr(row_scale), _ptr(bias), _ptr(norm_g), _ptr(ss)
+        a.ss_stride = ss_stride
+        a.act = act
+        a.residual = _ptr(residual)
+        a.ld_res = residual.shape[-1] if residual is not None else 0
+        a.out = out.data_ptr()
+        a.out_f32_nchw = 1 if out_f32_nchw else 0
+        if out_f32_nchw:
+            a.ld_out = 0
+            a.OH, a.OW = out.shape[2], out.shape[3]
+        else:
+            a.ld_out = out.shape[-1]
+            a.OH, a.OW = out.shape[1], out.shape[2]
+        a.sy, a.sx, a.oy, a.ox = out_map
+        a.rnorm_out = _ptr(rnorm_out)
+        self._keep.append(a)
+        fn = self.lib.ddm_conv2d
+        ref = C.byref(a)
+        (into if into is not None else self.ops).append((tag, lambda s, fn=fn, ref=ref: fn(ref, s)))
+
+    def _add(self, tag: str, fn: Callable[[int], int], into=None):
+        (into if into is not None else self.ops).append((tag, fn))
+
+    # ------------------------------------------------------------------ plan
+    def _build(self):
+        sp, B, H, W, lib, dev = self.spec, self.B, self.H, self.W, self.lib, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # ---- static I/O (fp32 NCHW like the reference's tensors)
+        self.x = torch.zeros((B, sp.channels, H, W), **f32)
+        self.x_self_cond = torch.zeros((B, sp.channels, H, W), **f32) if sp.self_condition else None
+        self.cond = torch.zeros((B, sp.cond_channels, H, W), **f32) if sp.cond_channels else None
+        self.out = torch.zeros((B, sp.out_dim, H, W), **f32)
+        self.time = torch.zeros((self.time_rows,), **f32)
+
+        # ---- time path (dd:280-285 + per-block mlp dd:127-130, tc:146-152) -> one [rows, sum 2C] table
+        blocks = sp.res_blocks()
+        self.ss_offsets, off = {}, 0
+        for rb in blocks:
+            self.ss_offsets[rb.name] = off
+            off += 2 * rb.c_out
+        self.ss_width = off
+        R = self.time_rows
+        self.ss = torch.zeros((R, self.ss_width), **f32)
+        self.ss_stride = self.ss_width if R == B and B > 1 else 0
+        self._build_time_path(self.time, self.ss, R, self.time_ops)
+
+        # ---- stem (dd:356-357; ic:52-54 cat(x, cond); dd:352-354 cat(self_cond, x))
+        stem_w = self._dev(pack_stem(self._w["init_conv.weight"]))
+        stem_b = self._f32("init_conv.bias")
+        ins = []
+        if sp.self_condition:
+            ins.append((self.x_self_cond, sp.channels))
+        ins.append((self.x, sp.channels))
+        if sp.cond_channels:
+            ins.append((self.cond, sp.cond_channels))
+        while len(ins) < 3:
+            ins.append((None, 0))
+        h0 = self._act(B, H, W, sp.init_dim, "init_conv")
+        self._add("init_conv", lambda s: lib.ddm_stem_conv(
+            _ptr(ins[0][0]), ins[0][1], _ptr(ins[1][0]), ins[1][1], _ptr(ins[2][0]), ins[2][1], stem_w.data_ptr(),
+            stem_b.data_ptr(), h0.data_ptr(), B, H, W, sp.init_dim, sp.stem_kernel, s))
+
+        # ---- text path for cross attention: K/V projections are loop-invariant (tc:63-65) -> text_ops
+        if sp.text_mode == "xattn":
+            m = max(self.text_tokens, 1)
+            self.text = torch.zeros((B, m, sp.text_emb_dim), dtype=torch.bfloat16, device=dev)
+            self.text_kv = {}
+            inner = sp.xattn_heads * sp.xattn_dim_head
+            for nm in ("cross_attn_down", "cross_attn", "cross_attn_up"):
+                kv = []
+                for proj in ("to_k", "to_v"):
+                    o = self._act(1, 1, B * m, inner)
+                    self._conv(f"{nm}.{proj}", pack_linear(self._w[f"{nm}.{proj}.weight"]),
+                               [self.text.view(1, 1, B * m, sp.text_emb_dim)], o, domain=(1, 1, B * m), into=self.text_ops)
+                    kv.append(o)
+                self.text_kv[nm] = kv
+        elif sp.text_mode == "concat":
+            self.text = torch.zeros((B, sp.text_emb_dim), **f32)
+        else:
+            self.text = None
+
+        # ---- body
+        x, h, w = h0, H, W
+        skips: List[torch.Tensor] = []
+        for st in sp.downs:
+            x = self._resblock(st.block1, [x], h, w); skips.append(x)
+            x = self._resblock(st.block2, [x], h, w, want_rnorm=True)
+            x = self._attention(st.attn, x, h, w); skips.append(x)
+            x, h, w = self._resample(st, x, h, w)
+        if sp.text_mode == "xattn":
+            x = self._cross_attention("cross_attn_down", x, h, w)
+        x = self._resblock(sp.mid1, [x], h, w, want_rnorm=(sp.text_mode != "xattn"))
+        if sp.text_mode == "xattn":
+            x = self._cross_attention("cross_attn", x, h, w)
+        x = self._attention(sp.mid_attn, x, h, w)
+        x = self._resblock(sp.mid2, [x], h, w)
+        if sp.text_mode == "xattn":
+            x = self._cross_attention("cross_attn_up", x, h, w)
+        for st in sp.ups:
+            x = self._resblock(st.block1, [x, skips.pop()], h, w)
+            x = self._resblock(st.block2, [x, skips.pop()], h, w, want_rnorm=True)
+            x = self._attention(st.attn, x, h, w)
+            x, h, w = self._resample(st, x, h, w)
+        x = self._resblock(sp.final_block, [x, h0], h, w)
+        self._conv("final_conv", pack_conv(self._w["final_conv.weight"]), [x], self.out, domain=(B, h, w),
+                   bias=self._f32("final_conv.bias"), out_f32_nchw=True)
+
+    def _build_time_path(self, t_in: torch.Tensor, ss_out: torch.Tensor, rows: int, into):
+        """sinusoid -> Linear -> GELU -> Linear [-> text concat] -> (SiLU -> Linear) for all blocks at once."""
+        sp, lib, dev = self.spec, self.lib, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        td = sp.time_dim
+        sin = torch.zeros((rows, sp.fourier_dim), **f32)
+        hid = torch.zeros((rows, td), **f32)
+        temb = torch.zeros((rows, td), **f32)
+        self._keep += [sin, hid, temb]
+        w1, b1 = self._f32("time_mlp.1.weight"), self._f32("time_mlp.1.bias")
+        w2, b2 = self._f32("time_mlp.3.weight"), self._f32("time_mlp.3.bias")
+        self._add("time.sin", lambda s: lib.ddm_sinusoidal_embedding(t_in.data_ptr(), sin.data_ptr(), rows, sp.fourier_dim,
+                                                                     sp.theta, s), into)
+        self._add("time.l1", lambda s: lib.ddm_small_linear(sin.data_ptr(), sp.fourier_dim, w1.data_ptr(), b1.data_ptr(),
+                                                            hid.data_ptr(), td, rows, td, sp.fourier_dim, 0, 2, s), into)
+        self._add("time.l2", lambda s: lib.ddm_small_linear(hid.data_ptr(), td, w2.data_ptr(), b2.data_ptr(),
+                                                            temb.data_ptr(), td, rows, td, td, 0, 0, s), into)
+        self.t_emb = temb
+        if sp.text_mode == "concat":
+            assert rows == self.B, "text-concat conditioning makes the time embedding per-sample: time_rows must be batch"
+            # t = text_concat_proj(cat(t, text_proj(text)))   (tc:146-152)
+            cat = torch.zeros((rows, 2 * td), **f32)
+            th = torch.zeros((rows, td), **f32)
+            t2 = torch.zeros((rows, td), **f32)
+            self._keep += [cat, th, t2]
+            pw0, pb0 = self._f32("text_proj.0.weight"), self._f32("text_proj.0.bias")
+            pw2, pb2 = self._f32("text_proj.2.weight"), self._f32("text_proj.2.bias")
+            cw, cb = self._f32("text_concat_proj.weight"), self._f32("text_concat_proj.bias")
+            self._text_concat = True
+            # re-point the second time linear at the first half of `cat`
+            into.pop()
+            self._add("time.l2", lambda s: lib.ddm_small_linear(hid.data_ptr(), td, w2.data_ptr(), b2.data_ptr(),
+                                                                cat.data_ptr(), 2 * td, rows, td, td, 0, 0, s), into)
+            self._add("text.p0", lambda s: lib.ddm_small_linear(self.text.data_ptr(), sp.text_emb_dim, pw0.data_ptr(),
+                                                                pb0.data_ptr(), th.data_ptr(), td, rows, td,
+                                                                sp.text_emb_dim, 0, 2, s), into)
+            self._add("text.p2", lambda s: lib.ddm_small_linear(th.data_ptr(), td, pw2.data_ptr(), pb2.data_ptr(),
+                                                                cat.data_ptr() + td * 4, 2 * td, rows, td, td, 0, 0, s), into)
+            self._add("text.cat", lambda s: lib.ddm_small_linear(cat.data_ptr(), 2 * td, cw.data_ptr(), cb.data_ptr(),
+                                                                 t2.data_ptr(), td, rows, td, 2 * td, 0, 0, s), into)
+            temb = t2
+            self.t_emb = t2
+        blocks = sp.res_blocks()
+        wss = self._dev(torch.cat([self._w[rb.name + ".mlp.1.weight"].float() for rb in blocks], dim=0))
+        bss = self._dev(torch.cat([self._w[rb.name + ".mlp.1.bias"].float() for rb in blocks], dim=0))
+        width = ss_out.shape[1]
+        self._add("time.ss", lambda s: lib.ddm_small_linear(temb.data_ptr(), td, wss.data_ptr(), bss.data_ptr(),
+                                                            ss_out.data_ptr(), width, rows, width, td, 1, 0, s), into)
+
+    def _block_tail(self, tag, pk, srcs, out, h, w, *, bias, g, ss, act, residual, rnorm_out=None):
+        """conv -> RMSNorm -> scale/shift -> act -> (+residual): fused into the conv epilogue when the output row
+        fits one TMEM tile, otherwise conv(+bias) followed by the row-norm kernel."""
+        B, lib = self.B, self.lib
+        c = pk.n
+        if c <= MAX_FUSED_NORM:
+            self._conv(tag, pk, srcs, out, domain=(B, h, w), bias=bias, norm_g=g, ss=ss, ss_stride=self.ss_stride,
+                       act=act, residual=residual, rnorm_out=rnorm_out)
+            return
+        tmp = self._act(B, h, w, c)
+        self._conv(tag + ".gemm", pk, srcs, tmp, domain=(B, h, w), bias=bias)
+        rows = B * h * w
+        self._add(tag + ".norm", lambda s: lib.ddm_rmsnorm_act(tmp.data_ptr(), _ptr(g), _ptr(ss), self.ss_stride, h * w, act,
+                                                                _ptr(residual), out.data_ptr(), rows, c, s))
+        if rnorm_out is not None:
+            self._add(tag + ".rnorm", lambda s: lib.ddm_row_rnorm(out.data_ptr(), c, rnorm_out.data_ptr(), rows, c, s))
+
+    def _resblock(self, rb: ResBlockSpec, srcs: List[torch.Tensor], h: int, w: int, want_rnorm: bool = False) -> torch.Tensor:
+        """ResnetBlock.forward, dd:136-148."""
+        B, W_ = self.B, self._w
+        split = rb.split if len(srcs) > 1 else None
+        ss = self.ss[:, self.ss_offsets[rb.name]:]
+        h1 = self._act(B, h, w, rb.c_out)
+        self._block_tail(rb.name + ".block1", pack_conv(W_[rb.name + ".block1.proj.weight"], split), srcs, h1, h, w,
+                         bias=self._f32(rb.name + ".block1.proj.bias"), g=self._dev(norm_gain(W_[rb.name + ".block1.norm.g"])),
+                         ss=ss, act=1, residual=None)
+        if rb.c_in != rb.c_out:
+            res = self._act(B, h, w, rb.c_out)
+            self._conv(rb.name + ".res_conv", pack_conv(W_[rb.name + ".res_conv.weight"], split), srcs, res,
+                       domain=(B, h, w), bias=self._f32(rb.name + ".res_conv.bias"))
+        else:
+            res = srcs[0]
+        out = self._act(B, h, w, rb.c_out, rb.name)
+        rn = None
+        if want_rnorm and self.fuse_rnorm:
+            rn = torch.zeros((B * h * w,), dtype=torch.float32, device=self.device)
+            self._keep.append(rn)
+        self._block_tail(rb.name + ".block2", pack_conv(W_[rb.name + ".block2.proj.weight"]), [h1], out, h, w,
+                         bias=self._f32(rb.name + ".block2.proj.bias"), g=self._dev(norm_gain(W_[rb.name + ".block2.norm.g"])),
+                         ss=None, act=1, residual=res, rnorm_out=rn)
+        self._last_rnorm = (out, rn)
+        return out
+
+    def _attention(self, at: AttnSpec, x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+        """`attn(x) + x` with LinearAttention (dd:173-193) or Attention (dd:215-229)."""
+        B, lib, W_ = self.B, self.lib, self._w
+        n, hid, c = h * w, at.heads * at.dim_head, at.dim
+        rows = B * n
+        last_out, rn = getattr(self, "_last_rnorm", (None, None))
+        if last_out is not x or rn is None:
+            rn = torch.zeros((rows,), dtype=torch.float32, device=self.device)
+            self._keep.append(rn)
+            self._add(at.name + ".rnorm", lambda s: lib.ddm_row_rnorm(x.data_ptr(), c, rn.data_ptr(), rows, c, s))
+        # pre-norm folded into the qkv GEMM: W (x * g sqrt(C) / |x|) = rnorm[pixel] * ((W diag(g sqrt(C))) x)
+        qkv = self._act(B, h, w, 3 * hid)
+        self._conv(at.name + ".to_qkv", pack_conv(W_[at.name + ".to_qkv.weight"], in_scale=norm_gain(W_[at.name + ".norm.g"])),
+                   [x], qkv, domain=(B, h, w), row_scale=rn)
+        a = self._act(B, h, w, hid)
+        mem = self._dev(W_[at.name + ".mem_kv"].float())
+        if at.full:
+            mk, mv = mem[0], mem[1]
+            self._add(at.name + ".attend", lambda s: lib.ddm_attention(
+                qkv.data_ptr(), 3 * hid, qkv.data_ptr() + hid * 2, 3 * hid, qkv.data_ptr() + 2 * hid * 2, 3 * hid,
+                mk.data_ptr(), mv.data_ptr(), at.n_mem, a.data_ptr(), B, n, n, at.heads, at.dim_head, s))
+            out = self._act(B, h, w, c, at.name)
+            self._conv(at.name + ".to_out", pack_conv(W_[at.name + ".to_out.weight"]), [a], out, domain=(B, h, w),
+                       bias=self._f32(at.name + ".to_out.bias"), residual=x)
+        else:
+            self._add(at.name + ".attend", lambda s: lib.ddm_linear_attention(
+                qkv.data_ptr(), mem.data_ptr(), a.data_ptr(), B, n, at.heads, at.dim_head, at.n_mem, s))
+            out = self._act(B, h, w, c, at.name)
+            self._block_tail(at.name + ".to_out", pack_conv(W_[at.name + ".to_out.0.weight"]), [a], out, h, w,
+                             bias=self._f32(at.name + ".to_out.0.bias"), g=self._dev(norm_gain(W_[at.name + ".to_out.1.g"])),
+                             ss=None, act=0, residual=x)
+        return out
+
+    def _cross_attention(self, nm: str, x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+        """CrossAttention (tc:54-78) on the flattened bottleneck; the result replaces x (tc:176-177)."""
+        sp, B, lib, W_ = self.spec, self.B, self.lib, self._w
+        n, c, m = h * w, x.shape[-1], max(self.text_tokens, 1)
+        inner, heads, d = sp.xattn_heads * sp.xattn_dim_head, sp.xattn_heads, sp.xattn_dim_head
+        q = self._act(B, h, w, inner)
+        self._conv(nm + ".to_q", pack_linear(W_[nm + ".to_q.weight"]), [x], q, domain=(B, h, w))
+        k, v = self.text_kv[nm]
+        a = self._act(B, h, w, inner)
+        self._add(nm + ".attend", lambda s: lib.ddm_attention(q.data_ptr(), inner, k.data_ptr(), inner, v.data_ptr(), inner,
+                                                              None, None, 0, a.data_ptr(), B, n, m, heads, d, s))
+        out = self._act(B, h, w, c, nm)
+        self._block_tail(nm + ".to_out", pack_linear(W_[nm + ".to_out.0.weight"]), [a], out, h, w,
+                         bias=self._f32(nm + ".to_out.0.bias"), g=self._dev(norm_gain(W_[nm + ".to_out.1.g"])),
+                         ss=None, act=0, residual=None)
+        return out
+
+    def _resample(self, st: StageSpec, x: torch.Tensor, h: int, w: int):
+        B, W_ = self.B, self._w
+        bias = self._f32(st.resample + ".bias")
+        if st.resample_kind == "down":                      # dd:54-58
+            out = self._act(B, h // 2, w // 2, st.c_res_out, st.resample)
+            self._conv(st.resample, pack_downsample(W_[st.resample + ".weight"]), [x], out, domain=(B, h // 2, w // 2), bias=bias)
+            return out, h // 2, w // 2
+        if st.resample_kind == "up":                        # dd:48-52, four sub-pixel phases
+            out = self._act(B, 2 * h, 2 * w, st.c_res_out, st.resample)
+            for pk, ph, pw in pack_upsample(W_[st.resample + ".weight"]):
+                self._conv(f"{st.resample}.p{ph}{pw}", pk, [x], out, domain=(B, h, w), bias=bias, out_map=(2, 2, ph, pw))
+            return out, 2 * h, 2 * w
+        out = self._act(B, h, w, st.c_res_out, st.resample)      # dd:319,336 plain 3x3
+        self._conv(st.resample, pack_conv(W_[st.resample + ".weight"]), [x], out, domain=(B, h, w), bias=bias)
+        return out, h, w
+
+    def build_step_table(self, tvals: torch.Tensor) -> torch.Tensor:
+        """Scale/shift rows for every timestep of a sampling loop, [S, ss_width]; valid because all samples share t."""
+        rows = int(tvals.numel())
+        table = torch.zeros((rows, self.ss_width), dtype=torch.float32, device=self.device)
+        ops: List[Tuple[str, Callable[[int], int]]] = []
+        keep_from = len(self._keep)
+        self._build_time_path(tvals.contiguous(), table, rows, ops)
+        self._run(ops)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        del self._keep[keep_from:]                 # temporaries of this one-off launch sequence
+        return table
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, ops, stream: Optional[int] = None):
+        if stream is not None:
+            s = stream
+        else:
+            s = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+        for tag, fn in ops:
+            rc = fn(s)
+            if rc != 0:
+                _lib.check(rc, tag)
+
+    def run_time_path(self, stream=None):
+        self._run(self.time_ops, stream)
+
+    def run_text_path(self, stream=None):
+        self._run(self.text_ops, stream)
+
+    def run_body(self, stream=None):
+        self._run(self.ops, stream)
+
+    @property
+    def launches_per_forward(self) -> int:
+        return len(self.ops)

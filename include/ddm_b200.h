@@ -1,0 +1,161 @@
+/*
+ * ddm_b200.h -- C ABI of libddm_b200.so: the B200 (sm_100a) kernels behind the denoising hot path of
+ * lbarseghyan/diffusion-models (U-Net eps-prediction forward inside the DDPM / DDIM / LDM sampling loop).
+ *
+ * The reference is pure Python/PyTorch and has no FFI; its "plugin boundary" for this path is the set of ATen ops
+ * its modules call.  Each entry point below replaces the op sites cited next to it (paths relative to
+ * /root/reference/denoising-diffusion-pytorch/denoising_diffusion/; dd = denoising_diffusion.py,
+ * tc = denoising_diffusion_text_conditional.py, at = attend.py).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a CUDA device pointer unless stated otherwise;
+ *   - activations are bf16, channels-last ([B, H, W, C], C contiguous); sampler state (x_t, eps) is fp32 NCHW
+ *     exactly like the reference's tensors;
+ *   - every launch goes to the caller's stream (`stream` is a cudaStream_t passed as void*), never synchronises,
+ *     never allocates, and is CUDA-graph capturable;
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative DDM_E_* code.
+ *   - there is no CPU fallback: without a B200 the library loads (so the symbols can be checked) but ddm_init fails.
+ */
+#ifndef DDM_B200_H_
+#define DDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDM_ABI_VERSION 1
+
+#define DDM_E_NOT_INITIALISED (-1)
+#define DDM_E_BAD_ARGUMENT (-2)
+#define DDM_E_UNSUPPORTED (-3)
+#define DDM_E_ALIGNMENT (-4)
+#define DDM_E_DRIVER (-5)
+#define DDM_E_WRONG_ARCH (-6)
+
+#define DDM_MAX_TAPS 9
+
+int ddm_abi_version(void);
+/* Must be called once per process per device before any launch: resolves cuTensorMapEncodeTiled, checks for
+ * compute capability 10.x, raises the dynamic shared-memory limits. */
+int ddm_init(int device);
+const char* ddm_error_string(int code);
+/* Kernel launches issued through this library since ddm_init (bench.py's gpu_launches claim). */
+long long ddm_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K1/K2: implicit-GEMM convolution on tcgen05 with the block epilogue fused.
+ * Replaces: nn.Conv2d 3x3 in Block.proj (dd:108,114), stage-end 3x3 convs (dd:319,336), Upsample conv (dd:48-52,
+ * as four sub-pixel phases), Downsample unshuffle + 1x1 (dd:54-58, view = 1), res_conv / to_qkv / to_out /
+ * final_conv 1x1 (dd:134,166,169,212,213,343), nn.Linear over token matrices (tc:45-52), and the ops fused behind
+ * them: RMSNorm (dd:60-67), scale/shift (dd:117-119), SiLU (dd:121), residual add (dd:148,368), torch.cat of skip
+ * connections (dd:378,381,387) as a second source.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct ddm_conv_args {
+    /* sources: bf16 channels-last, same pixel grid, concatenated along channels (src1 may be NULL) */
+    const void* src0;
+    const void* src1;
+    int C0, C1;         /* channels read from each source (multiples of 8)                                    */
+    int ld0, ld1;       /* elements between consecutive pixels of each source (>= C)                          */
+    int view;           /* 0: source is [B,H,W,C]; 1: source is [B,2H,2W,C] read as [B,H,W,(p1),(p2 c)]:      *
+                         *    tap_p selects p1, the channel axis is (p2, c) of length 2C (pixel-unshuffle)      */
+    int B, H, W;        /* tile domain: one GEMM row per (b, y, x)                                             */
+    int ntaps;
+    int tap_dy[DDM_MAX_TAPS];
+    int tap_dx[DDM_MAX_TAPS];
+    int tap_p[DDM_MAX_TAPS];
+    /* packed weights: bf16 [N_pad][K_pad], K contiguous, K order = (tap, source, channel) with each
+     * (tap, source) segment zero-padded to a multiple of 64; N_pad = N rounded up to 16 */
+    const void* weight;
+    int N, N_pad, K_pad;
+    /* epilogue, applied in this order */
+    const float* row_scale;    /* [B*H*W] or NULL: acc *= row_scale[pixel]  (attention pre-norm, dd:176,218)   */
+    const float* bias;         /* [N] or NULL                                                                   */
+    const float* norm_g;       /* [N] (g * sqrt(N)) or NULL: RMSNorm over the N outputs of a pixel; N <= 256  */
+    const float* scale_shift;  /* [Bt][2N] or NULL: v = v * (scale + 1) + shift                                 */
+    long long ss_stride;       /* elements between batch rows of scale_shift; 0 = all rows share row 0         */
+    int act;                   /* 0 = none, 1 = SiLU                                                            */
+    const void* residual;      /* bf16, addressed like `out`, added last; or NULL                              */
+    int ld_res;
+    void* out;
+    int out_f32_nchw;          /* 0: bf16 [B,OH,OW,ld_out]; 1: fp32 [B,N,OH,OW]                                 */
+    int ld_out;
+    int OH, OW, oy, ox, sy, sx; /* tile pixel (b,y,x) is stored at (b, y*sy+oy, x*sx+ox)                        */
+    float* rnorm_out;          /* [B*OH*OW] or NULL: 1/max(||stored row||, 1e-12) for a following pre-norm     */
+} ddm_conv_args;
+
+int ddm_conv2d(const ddm_conv_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K3: stem convolution (dd:262,356; ic:46-54).  Direct k x k conv (k = 7, pad 3) over the channel-concatenation
+ * of up to three fp32 NCHW tensors, written as bf16 channels-last.  weight: fp32 [k*k*Cin][Cout] (tap-major).
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* weight,
+                  const float* bias, void* out_bf16, int B, int H, int W, int Cout, int ksize, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K5: time-conditioning path (dd:77-84 sinusoid, dd:280-285 time_mlp, dd:127-130 per-block SiLU -> Linear,
+ * tc:146-152 text concat).  Built from two tiny kernels.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* out[r, :] = cat(sin(t_r f), cos(t_r f)), f_j = exp(-j ln(theta)/(half-1)); t is fp32 [rows] */
+int ddm_sinusoidal_embedding(const float* t, float* out, int rows, int dim, float theta, void* stream);
+/* y[r, n] = act_out( sum_k act_in(x[r, k]) W[n, k] + b[n] ); W fp32 [N][K] (nn.Linear layout).
+ * act codes: 0 none, 1 SiLU, 2 exact-erf GELU.  x has row stride ldx, y has row stride ldy. */
+int ddm_small_linear(const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int rows, int N, int K,
+                     int act_in, int act_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K4: row norms (dd:60-67).  rnorm[m] = 1/max(||x[m,:]||_2, 1e-12) over C bf16 channels (row stride ld).
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddm_row_rnorm(const void* x_bf16, int ld, float* rnorm, long long rows, int C, void* stream);
+/* Unfused Block tail for C_out > 256: out = [ +residual ] act( RMSNorm(x) * (scale+1) + shift ), all bf16 rows of
+ * length C (dd:115-122,148; tc:27-36 RMSNorm1D).  rows_per_batch maps a row to its scale_shift row. */
+int ddm_rmsnorm_act(const void* x_bf16, const float* norm_g, const float* scale_shift, long long ss_stride,
+                    long long rows_per_batch, int act, const void* residual_bf16, void* out_bf16, long long rows, int C,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K6: linear attention core (dd:178-192).  qkv: bf16 [B, n, 3*heads*d] (q | k | v, head-major channels),
+ * mem_kv: fp32 [2][heads][d][n_mem] (dd:163); out: bf16 [B, n, heads*d].  d must be 16, 32 or 64.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddm_linear_attention(const void* qkv_bf16, const float* mem_kv, void* out_bf16, int B, int n, int heads, int d,
+                         int n_mem, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K7/K8: softmax attention (dd:220-228 + at:109-124; tc:66-77).  q: bf16 rows [B*nq] with row stride ldq, head h at
+ * column h*d; k, v likewise over [B*nk] rows; optional learned memory rows mem_k/mem_v fp32 [heads][n_mem][d] are
+ * prepended to the keys/values (dd:223-224).  out: bf16 [B*nq][heads*d].  scale = d^-0.5.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddm_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const float* mem_k,
+                  const float* mem_v, int n_mem, void* out_bf16, int B, int nq, int nk, int heads, int d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K9: per-timestep sampler update, one fused elementwise kernel (dd:603-626 model_predictions, dd:684-701 DDIM,
+ * dd:628-645 + dd:594-601 ancestral DDPM).  State tensors are fp32 NCHW with `numel` elements.  The per-step
+ * coefficients live in a device table so that one captured CUDA graph can be replayed for every step:
+ * row s of `coef` (8 floats) is selected by *step_counter (device int32), which the kernel increments when
+ * `advance` != 0.
+ *   DDIM row : { sqrt_recip_acp[t], sqrt_recipm1_acp[t], sqrt(acp[t_next]), c, sigma, is_last, sqrt_acp[t], sqrt_1m_acp[t] }
+ *   DDPM row : { sqrt_recip_acp[t], sqrt_recipm1_acp[t], coef1[t], coef2[t], exp(0.5 logvar[t]) or 0 at t=0, 0,
+ *                sqrt_acp[t], sqrt_1m_acp[t] }
+ * objective: 0 pred_noise, 1 pred_x0, 2 pred_v.  noise: fp32, the draw of step s starts at noise + s*noise_step_stride
+ * (injected noise, parity mode), or NULL to draw N(0,1) in-kernel from Philox4x32-10 keyed by (seed, step, element);
+ * x_start_out may be NULL.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define DDM_SAMPLER_DDIM 0
+#define DDM_SAMPLER_DDPM 1
+int ddm_sampler_step(int kind, float* x, const float* model_out, const float* noise, long long noise_step_stride,
+                     float* x_start_out, const float* coef, int* step_counter, int advance, int objective, unsigned long long seed,
+                     long long numel, void* stream);
+/* y = (x + 1) * 0.5 (utils.py:48-49) or a plain copy when unnormalize == 0 */
+int ddm_finalize(const float* x, float* y, int unnormalize, long long numel, void* stream);
+/* dst[i] = src[(*step_counter) * row_len + i]: selects the current step's row of a precomputed per-step table */
+int ddm_select_row(const float* table, const int* step_counter, float* dst, int row_len, void* stream);
+/* x ~ N(0,1) from the library's Philox stream (throughput mode x_T, dd:651,676) */
+int ddm_randn(float* x, unsigned long long seed, unsigned long long stream_id, long long numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDM_B200_H_ */
