@@ -307,10 +307,15 @@ class DenoisingDiffusion(nn.Module):
                 eng.x_self_cond.zero_()
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(dev)
+            n0 = _lib.launch_count()
             with torch.cuda.graph(graph):
                 step_ops(torch.cuda.current_stream(dev).cuda_stream)
+            per_step = _lib.launch_count() - n0
             for _ in range(S):
                 graph.replay()
+            # kernels executed by replays that did not pass through the C-ABI counter (the captured pass itself did
+            # pass through the counter but was recorded, not executed)
+            self._last_graph_launches = per_step * (S - 1)
             eng._graph_keepalive = (graph, key_state)
         ret = eng.x.clone() if imgs is None else torch.stack(imgs, dim=1)
         out = torch.empty_like(ret)

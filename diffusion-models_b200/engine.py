@@ -34,7 +34,7 @@ class UnetEngine:
         assert time_rows in (1, batch)
         self.spec, self.B, self.H, self.W = spec, batch, height, width
         self.device = torch.device(device)
-        # `lib` is a test seam (tests/fake_lib.py executes a plan with torch ops to check the host logic on CPU);
+        # `lib` is a test seam (the CPU test-suite injects a stand-in that checks the host logic of a plan);
         # the product always binds the real shared library and needs a B200.
         if lib is not None:
             self.lib = lib

@@ -1,0 +1,314 @@
+"""Per-kernel parity on a B200: every C-ABI entry point of include/ddm_b200.h against tests/kernel_ref.py on random
+inputs (bit-level rounding aside: bf16 outputs are compared with rtol/atol of one bf16 ulp-ish, 1e-2)."""
+import ctypes as C
+
+import pytest
+import torch
+
+import kernel_ref as R
+
+pytestmark = pytest.mark.gpu
+
+BF, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from diffusion_models_b200 import _lib
+    return _lib.init(0)
+
+
+def dev(t, dtype=None):
+    return t.to("cuda", dtype or t.dtype).contiguous()
+
+
+def rnd(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(code):
+    from diffusion_models_b200 import _lib
+    _lib.check(code)
+    torch.cuda.synchronize()
+
+
+def close(a, b, tol=1e-2):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    bound = tol * b.abs() + tol
+    bad = (err > bound).float().mean().item()
+    assert bad < 1e-4, f"{bad * 100:.3f}% elements off; max err {err.max().item():.4f}; rel-l2 {(a - b).norm() / b.norm():.4e}"
+
+
+def run_conv(lib, srcs, pk, domain, out, **kw):
+    """srcs: list of device bf16 tensors [B,Hs,Ws,C]; pk: PackedConv.  Returns (kernel out, reference out)."""
+    from diffusion_models_b200._lib import ConvArgs
+    w = dev(pk.weight)
+    a = ConvArgs()
+    a.src0 = srcs[0].data_ptr()
+    a.src1 = srcs[1].data_ptr() if len(srcs) > 1 else None
+    a.C0 = pk.seg_channels[0] // (2 if pk.view else 1)
+    a.C1 = pk.seg_channels[1] if len(srcs) > 1 else 0
+    a.ld0 = srcs[0].shape[-1]
+    a.ld1 = srcs[1].shape[-1] if len(srcs) > 1 else 0
+    a.view = pk.view
+    a.B, a.H, a.W = domain
+    a.ntaps = len(pk.taps)
+    for i, (dy, dx, p) in enumerate(pk.taps):
+        a.tap_dy[i], a.tap_dx[i], a.tap_p[i] = dy, dx, p
+    a.weight = w.data_ptr()
+    a.N, a.N_pad, a.K_pad = pk.n, pk.n_pad, pk.k_pad
+    ptr = lambda t: None if t is None else t.data_ptr()
+    a.row_scale, a.bias, a.norm_g = ptr(kw.get("row_scale")), ptr(kw.get("bias")), ptr(kw.get("norm_g"))
+    ss = kw.get("scale_shift")
+    a.scale_shift = ptr(ss)
+    a.ss_stride = ss.shape[1] if (ss is not None and ss.shape[0] > 1) else 0
+    a.act = kw.get("act", 0)
+    res = kw.get("residual")
+    a.residual, a.ld_res = ptr(res), (res.shape[-1] if res is not None else 0)
+    nchw = kw.get("out_f32_nchw", False)
+    a.out, a.out_f32_nchw = out.data_ptr(), int(nchw)
+    if nchw:
+        a.ld_out, a.OH, a.OW = 0, out.shape[2], out.shape[3]
+    else:
+        a.ld_out, a.OH, a.OW = out.shape[-1], out.shape[1], out.shape[2]
+    a.sy, a.sx, a.oy, a.ox = kw.get("out_map", (1, 1, 0, 0))
+    rn = kw.get("rnorm_out")
+    a.rnorm_out = ptr(rn)
+    check(lib.ddm_conv2d(C.byref(a), stream()))
+    ref_out = torch.zeros_like(out, dtype=F32)
+    ref_rn = torch.zeros_like(rn) if rn is not None else None
+    R.conv_ref([s.float() for s in srcs], w.float(), pk.n, domain, pk.taps, view=pk.view,
+               row_scale=kw.get("row_scale"), bias=kw.get("bias"), norm_g=kw.get("norm_g"), scale_shift=ss,
+               act=a.act, residual=res.float() if res is not None else None, out=ref_out, out_map=(a.sy, a.sx, a.oy, a.ox),
+               out_f32_nchw=nchw, rnorm_out=ref_rn)
+    return ref_out, ref_rn
+
+
+# ------------------------------------------------------------------------------------------------ conv kernel
+def test_gemm_1x1_plain(lib):
+    from diffusion_models_b200.packing import pack_conv
+    x = dev(rnd((2, 16, 16, 64), 1), BF)
+    pk = pack_conv(rnd((64, 64, 1, 1), 2, 0.125))
+    out = torch.zeros((2, 16, 16, 64), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (2, 16, 16), out)
+    close(out, ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 64, 64), (3, 16, 16, 128, 128), (4, 8, 8, 256, 256),
+                                             (9, 4, 4, 256, 256), (1, 64, 64, 64, 64), (1, 8, 24, 32, 32)])
+def test_conv3x3_block_epilogue(lib, B, H, W, Cin, Cout):
+    """Block.forward: conv -> RMSNorm -> scale/shift -> SiLU (+ residual, + row-norm side output)."""
+    from diffusion_models_b200.packing import pack_conv
+    x = dev(rnd((B, H, W, Cin), 3), BF)
+    pk = pack_conv(rnd((Cout, Cin, 3, 3), 4, (Cin * 9) ** -0.5))
+    bias, g = dev(rnd((Cout,), 5, 0.1)), dev(1 + 0.1 * rnd((Cout,), 6)) * Cout ** 0.5
+    ss = dev(rnd((B, 2 * Cout), 7, 0.3))
+    res = dev(rnd((B, H, W, Cout), 8), BF)
+    out = torch.zeros((B, H, W, Cout), dtype=BF, device="cuda")
+    rn = torch.zeros((B * H * W,), dtype=F32, device="cuda")
+    ref, ref_rn = run_conv(lib, [x], pk, (B, H, W), out, bias=bias, norm_g=g, scale_shift=ss, act=1, residual=res, rnorm_out=rn)
+    close(out, ref)
+    close(rn, ref_rn, 2e-2)
+
+
+def test_conv3x3_shared_scale_shift_row(lib):
+    from diffusion_models_b200.packing import pack_conv
+    B, H, W, Cin, Cout = 2, 16, 16, 64, 64
+    x = dev(rnd((B, H, W, Cin), 13), BF)
+    pk = pack_conv(rnd((Cout, Cin, 3, 3), 14, (Cin * 9) ** -0.5))
+    ss = dev(rnd((1, 2 * Cout), 17, 0.3))
+    out = torch.zeros((B, H, W, Cout), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (B, H, W), out, bias=dev(rnd((Cout,), 15, 0.1)), norm_g=dev(torch.full((Cout,), 8.0)),
+                      scale_shift=ss, act=1)
+    close(out, ref)
+
+
+def test_conv3x3_two_sources_concat(lib):
+    from diffusion_models_b200.packing import pack_conv
+    B, H, W = 2, 16, 16
+    a, b = dev(rnd((B, H, W, 128), 20), BF), dev(rnd((B, H, W, 64), 21), BF)
+    pk = pack_conv(rnd((128, 192, 3, 3), 22, (192 * 9) ** -0.5), split=(128, 64))
+    out = torch.zeros((B, H, W, 128), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [a, b], pk, (B, H, W), out, bias=dev(rnd((128,), 23, 0.1)))
+    close(out, ref)
+
+
+def test_conv_wide_output_two_n_tiles(lib):
+    """N = 384 (to_qkv, two 192-wide tiles, pre-norm row scale) and N = 512 (two 256-wide tiles)."""
+    from diffusion_models_b200.packing import pack_conv
+    B, H, W = 2, 8, 8
+    x = dev(rnd((B, H, W, 128), 30), BF)
+    rs = dev(torch.rand((B * H * W,), generator=torch.Generator().manual_seed(31)) + 0.5)
+    pk = pack_conv(rnd((384, 128, 1, 1), 32, 128 ** -0.5))
+    out = torch.zeros((B, H, W, 384), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (B, H, W), out, row_scale=rs)
+    close(out, ref)
+    x2 = dev(rnd((B, 4, 4, 256), 33), BF)
+    pk2 = pack_conv(rnd((512, 256, 3, 3), 34, (256 * 9) ** -0.5))
+    out2 = torch.zeros((B, 4, 4, 512), dtype=BF, device="cuda")
+    ref2, _ = run_conv(lib, [x2], pk2, (B, 4, 4), out2, bias=dev(rnd((512,), 35, 0.1)))
+    close(out2, ref2)
+
+
+def test_downsample_unshuffle_view(lib):
+    from diffusion_models_b200.packing import pack_downsample
+    B, H, W, C_, Co = 2, 16, 16, 64, 128           # source is [B,32,32,64]
+    x = dev(rnd((B, 2 * H, 2 * W, C_), 40), BF)
+    pk = pack_downsample(rnd((Co, 4 * C_, 1, 1), 41, (4 * C_) ** -0.5))
+    out = torch.zeros((B, H, W, Co), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (B, H, W), out, bias=dev(rnd((Co,), 42, 0.1)))
+    close(out, ref)
+    # and against the reference formulation itself: Rearrange + 1x1 conv (dd:54-58)
+    wt = rnd((Co, 4 * C_, 1, 1), 41, (4 * C_) ** -0.5).to(BF).float().cuda()
+    xn = x.float().permute(0, 3, 1, 2)
+    un = xn.reshape(B, C_, H, 2, W, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, 4 * C_, H, W)
+    y = torch.nn.functional.conv2d(un, wt, dev(rnd((Co,), 42, 0.1)))
+    close(out, y.permute(0, 2, 3, 1))
+
+
+def test_upsample_four_phases(lib):
+    from diffusion_models_b200.packing import pack_upsample
+    B, H, W, C_, Co = 2, 8, 8, 128, 64
+    x = dev(rnd((B, H, W, C_), 50), BF)
+    wt = rnd((Co, C_, 3, 3), 51, (C_ * 9) ** -0.5)
+    bias = dev(rnd((Co,), 52, 0.1))
+    out = torch.zeros((B, 2 * H, 2 * W, Co), dtype=BF, device="cuda")
+    for pk, ph, pw in pack_upsample(wt):
+        run_conv(lib, [x], pk, (B, H, W), out, bias=bias, out_map=(2, 2, ph, pw))
+    up = x.float().permute(0, 3, 1, 2).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    y = torch.nn.functional.conv2d(up, wt.cuda(), bias, padding=1)           # dd:48-52
+    close(out, y.permute(0, 2, 3, 1), 2e-2)
+
+
+def test_final_conv_fp32_nchw(lib):
+    from diffusion_models_b200.packing import pack_conv
+    B, H, W = 3, 32, 32
+    x = dev(rnd((B, H, W, 64), 60), BF)
+    pk = pack_conv(rnd((3, 64, 1, 1), 61, 0.125))
+    out = torch.zeros((B, 3, H, W), dtype=F32, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (B, H, W), out, bias=dev(rnd((3,), 62, 0.1)), out_f32_nchw=True)
+    close(out, ref, 2e-3)
+
+
+def test_token_gemm_ragged_rows(lib):
+    """nn.Linear over a [1,1,rows,K] token matrix whose row count is not a multiple of the 128-row tile."""
+    from diffusion_models_b200.packing import pack_linear
+    rows = 5 * 77
+    x = dev(rnd((1, 1, rows, 512), 70), BF)
+    pk = pack_linear(rnd((128, 512), 71, 512 ** -0.5))
+    out = torch.zeros((1, 1, rows, 128), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (1, 1, rows), out)
+    close(out, ref)
+
+
+def test_conv_persistent_many_tiles(lib):
+    """More tiles than SMs: exercises the persistent loop, smem ring wrap-around and both TMEM accumulator stages."""
+    from diffusion_models_b200.packing import pack_conv
+    B, H, W = 40, 32, 32          # 320 tiles
+    x = dev(rnd((B, H, W, 64), 80), BF)
+    pk = pack_conv(rnd((64, 64, 3, 3), 81, (64 * 9) ** -0.5))
+    out = torch.zeros((B, H, W, 64), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (B, H, W), out, bias=dev(rnd((64,), 82, 0.1)), norm_g=dev(torch.full((64,), 8.0)), act=1)
+    close(out, ref)
+
+
+# ------------------------------------------------------------------------------------------------ other kernels
+@pytest.mark.parametrize("cs", [(3, 0, 0), (4, 4, 0), (3, 3, 2)])
+def test_stem_conv(lib, cs):
+    from diffusion_models_b200.packing import pack_stem
+    B, H, W, Co = 2, 32, 40, 64
+    ins = [dev(rnd((B, c, H, W), 90 + i)) for i, c in enumerate(cs) if c]
+    cin = sum(cs)
+    wt = rnd((Co, cin, 7, 7), 95, (cin * 49) ** -0.5)
+    wp, bias = dev(pack_stem(wt)), dev(rnd((Co,), 96, 0.1))
+    out = torch.zeros((B, H, W, Co), dtype=BF, device="cuda")
+    p = [t.data_ptr() for t in ins] + [None] * (3 - len(ins))
+    c = [x for x in cs if x] + [0] * (3 - len(ins))
+    check(lib.ddm_stem_conv(p[0], c[0], p[1], c[1], p[2], c[2], wp.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Co, 7, stream()))
+    close(out, R.stem_ref(ins, wp, bias, 7, Co))
+
+
+def test_time_path_kernels(lib):
+    t = dev(torch.tensor([0.0, 17.0, 999.0, 500.0]))
+    emb = torch.zeros((4, 64), device="cuda")
+    check(lib.ddm_sinusoidal_embedding(t.data_ptr(), emb.data_ptr(), 4, 64, 10000.0, stream()))
+    assert (emb - R.sinusoidal_ref(t, 64, 10000.0)).abs().max().item() < 2e-4
+    x, W_, b = dev(rnd((4, 256), 100)), dev(rnd((300, 256), 101, 256 ** -0.5)), dev(rnd((300,), 102, 0.1))
+    for ai, ao in ((0, 0), (1, 0), (0, 2)):
+        y = torch.zeros((4, 300), device="cuda")
+        check(lib.ddm_small_linear(x.data_ptr(), 256, W_.data_ptr(), b.data_ptr(), y.data_ptr(), 300, 4, 300, 256, ai, ao, stream()))
+        assert (y - R.small_linear_ref(x, W_, b, ai, ao)).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("C_", [32, 64, 128, 256, 512])
+def test_row_norm_kernels(lib, C_):
+    rows = 1000
+    x = dev(rnd((rows, C_), 110), BF)
+    rn = torch.zeros((rows,), device="cuda")
+    check(lib.ddm_row_rnorm(x.data_ptr(), C_, rn.data_ptr(), rows, C_, stream()))
+    close(rn, R.row_rnorm_ref(x), 1e-4)
+    g, ss, res = dev(rnd((C_,), 111) * 0.1 + 1) * C_ ** 0.5, dev(rnd((4, 2 * C_), 112, 0.3)), dev(rnd((rows, C_), 113), BF)
+    out = torch.zeros((rows, C_), dtype=BF, device="cuda")
+    check(lib.ddm_rmsnorm_act(x.data_ptr(), g.data_ptr(), ss.data_ptr(), 2 * C_, 250, 1, res.data_ptr(), out.data_ptr(), rows, C_, stream()))
+    close(out, R.rmsnorm_act_ref(x.float(), g, ss, 250, 1, res.float()))
+
+
+@pytest.mark.parametrize("n,heads,d", [(1024, 4, 32), (64, 4, 32), (256, 2, 16), (100, 4, 64)])
+def test_linear_attention(lib, n, heads, d):
+    B = 3
+    qkv = dev(rnd((B, n, 3 * heads * d), 120), BF)
+    mem = dev(rnd((2, heads, d, 4), 121))
+    out = torch.zeros((B, n, heads * d), dtype=BF, device="cuda")
+    check(lib.ddm_linear_attention(qkv.data_ptr(), mem.data_ptr(), out.data_ptr(), B, n, heads, d, 4, stream()))
+    close(out, R.linear_attention_ref(qkv.float(), mem, heads, d), 2e-2)
+
+
+@pytest.mark.parametrize("nq,nk,heads,d,n_mem", [(16, 16, 4, 32, 4), (64, 64, 4, 32, 4), (256, 256, 4, 32, 4), (64, 77, 4, 32, 0),
+                                                 (16, 1, 4, 32, 0), (16, 16, 2, 16, 4)])
+def test_softmax_attention(lib, nq, nk, heads, d, n_mem):
+    B, hd = 3, heads * d
+    q, k, v = (dev(rnd((B, n_, hd), 130 + i), BF) for i, n_ in enumerate((nq, nk, nk)))
+    mk, mv = (dev(rnd((heads, max(n_mem, 1), d), 135 + i)) for i in range(2))
+    out = torch.zeros((B, nq, hd), dtype=BF, device="cuda")
+    check(lib.ddm_attention(q.data_ptr(), hd, k.data_ptr(), hd, v.data_ptr(), hd, mk.data_ptr() if n_mem else None,
+                            mv.data_ptr() if n_mem else None, n_mem, out.data_ptr(), B, nq, nk, heads, d, stream()))
+    close(out, R.attention_ref(q.float(), k.float(), v.float(), mk if n_mem else None, mv if n_mem else None, heads, d), 2e-2)
+
+
+@pytest.mark.parametrize("kind,objective", [(0, 0), (0, 1), (0, 2), (1, 0), (1, 2)])
+def test_sampler_step_bit_exact(lib, kind, objective):
+    """fp32 update must match the reference's unfused op chain bit for bit (no FMA contraction)."""
+    shape = (2, 3, 32, 32)
+    x, mo, z = dev(rnd(shape, 140)), dev(rnd(shape, 141)), dev(rnd((3,) + shape, 142))
+    coef = torch.tensor([[1.9, 1.6, 0.7, 0.6, 0.3, 0.0, 0.52, 0.85],
+                         [1.2, 0.66, 0.9, 0.4, 0.0, 0.0, 0.83, 0.55],
+                         [1.01, 0.14, 0.0, 0.0, 0.0, 1.0, 0.99, 0.14]], device="cuda")
+    counter = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    xs, x0 = x.clone(), torch.zeros_like(x)
+    ref = x.clone()
+    for s in range(3):
+        check(lib.ddm_sampler_step(kind, xs.data_ptr(), mo.data_ptr(), z.data_ptr(), x.numel(), x0.data_ptr(), coef.data_ptr(),
+                                   counter.data_ptr(), 1, objective, 0, x.numel(), stream()))
+        ref, ref0 = R.sampler_step_ref(kind, ref, mo, z[s], coef[s].cpu().tolist(), objective)
+        assert torch.equal(xs, ref), (s, (xs - ref).abs().max().item())
+        assert torch.equal(x0, ref0)
+    assert counter.item() == 3
+
+
+def test_philox_normal_statistics(lib):
+    n = 1 << 20
+    x = torch.zeros((n,), device="cuda")
+    check(lib.ddm_randn(x.data_ptr(), 1234, 0, n, stream()))
+    y = torch.zeros((n,), device="cuda")
+    check(lib.ddm_randn(y.data_ptr(), 1234, 1, n, stream()))
+    assert abs(x.mean().item()) < 5e-3 and abs(x.std().item() - 1) < 5e-3
+    assert abs((x * y).mean().item()) < 5e-3            # different streams are uncorrelated
+    assert abs((x ** 4).mean().item() - 3.0) < 0.05      # kurtosis of N(0,1)
+    out = torch.zeros((n,), device="cuda")
+    check(lib.ddm_finalize(x.data_ptr(), out.data_ptr(), 1, n, stream()))
+    assert torch.equal(out, (x + 1) * 0.5)
