@@ -155,7 +155,9 @@ def attention_ref(q, k, v, mem_k, mem_v, heads, d):
 
 
 def sampler_step_ref(kind, x, mo, noise, coef, objective):
-    """One row of the coefficient table applied like ddm_sampler_step (unfused fp32 ops in the reference's order)."""
+    """One row of the coefficient table applied like ddm_sampler_step (unfused fp32 ops in the reference's order).
+    `coef` must be a tensor: the reference divides by a (B,1,1,1) *tensor* (true division, dd:576-580), whereas torch
+    turns division by a Python scalar into a multiplication by its reciprocal."""
     ra, rm1, k2, k3, k4, k5, sac, s1m = (coef[i] for i in range(8))
     rax = ra * x
     if objective == 0:

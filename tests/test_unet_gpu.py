@@ -194,11 +194,26 @@ def test_self_condition_loop_and_latent_wrapper():
 
     d = LatentDiffusion(model, Vae(), (4, 16, 16), sampling_timesteps=4).cuda()
     xT = torch.randn((2, 4, 16, 16), generator=torch.Generator().manual_seed(9))
-    y = d.sample(batch_size=2, noise=xT.cuda())
+    # teacher-forced on the CUDA trajectory: at every step the oracle sees the same x_t and the same fed-back x_start
+    trace = []
+    y_eager = d.ddim_sample((2, 4, 16, 16), noise=xT.cuda(), trace=trace)
+    sch, prev_x0 = make_schedule(1000), None
+    for i, st in enumerate(trace):
+        tb = torch.full((2,), st["t"], dtype=torch.long)
+        with torch.inference_mode():
+            ref_out = unet_forward(sd, st["x_t"].cpu(), tb, cfg, x_self_cond=prev_x0)
+        assert rel_l2(st["model_out"], ref_out) < EPS_TOL, (i, rel_l2(st["model_out"], ref_out))
+        tn = ddim_time_pairs(1000, 4)[i][1]
+        ref_next, ref_x0 = ddim_update(sch, st["model_out"].cpu(), st["x_t"].cpu(), st["t"], tn, 0.0, None)
+        assert torch.equal(st["x_next"].cpu(), ref_next) and torch.equal(st["x_start"].cpu(), ref_x0)   # fp32 update is exact
+        prev_x0 = st["x_start"].cpu()
+    y = d.sample(batch_size=2, noise=xT.cuda())                     # graph replay + vae.decode
+    assert torch.equal(y, y_eager * 2.0)
     with torch.inference_mode():
         ref = oracle_ddim(lambda x, t, sc: unet_forward(sd, x, t, cfg, x_self_cond=sc), make_schedule(1000), xT, 4,
                           self_condition=True, unnormalize=False) * 2.0
-    assert rel_l2(y, ref) < 5e-2
+    # free-running with x_start fed back is a chaotic map under the +-1 clamp: only a loose bound is meaningful
+    assert rel_l2(y, ref) < 0.3
 
 
 def test_large_batch_properties():
