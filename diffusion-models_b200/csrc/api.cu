@@ -125,8 +125,14 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if (a->ntaps * (p.chunks0 + p.chunks1) * 64 != a->K_pad) return DDM_E_BAD_ARGUMENT;
     p.tmem_cols = pow2_ceil(2 * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
     p.acc_stride = p.tmem_cols / 2;
-    const int stage_bytes = ddm::kATileBytes + p.block_n * 128;
-    p.num_stages = (200 * 1024) / stage_bytes; if (p.num_stages > 8) p.num_stages = 8;
+    p.n_pad = a->N_pad;
+    if (p.n_pad > ddm::kMaxNPad) return DDM_E_UNSUPPORTED;
+    // bf16 tiles whose channel count is a multiple of 64 leave through smem staging + TMA stores
+    const bool strided_out = (a->sy != 1 || a->sx != 1);
+    if (strided_out && !(a->sy == 2 && a->sx == 2 && a->OH == 2 * a->H && a->OW == 2 * a->W)) return DDM_E_UNSUPPORTED;
+    p.tma_store = (!a->out_f32_nchw && (a->N % 64) == 0 && (!strided_out || a->ld_out == a->N) && a->OH >= a->H * a->sy &&
+                   a->OW >= a->W * a->sx) ? 1 : 0;
+    ddm::conv_smem_plan(p.block_n, p.n_pad, p.tma_store, &p.num_stages);
     p.bias = a->bias; p.row_scale = a->row_scale; p.norm_g = a->norm_g; p.scale_shift = a->scale_shift;
     p.ss_stride = a->ss_stride; p.act = a->act;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ld_res = a->ld_res;
@@ -134,7 +140,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.OH = a->OH; p.OW = a->OW; p.oy = a->oy; p.ox = a->ox; p.sy = a->sy; p.sx = a->sx;
     p.rnorm_out = a->rnorm_out;
 
-    CUtensorMap tmA0, tmA1, tmW;
+    CUtensorMap tmA0, tmA1, tmW, tmOut;
     const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};
     auto encode_src = [&](CUtensorMap* tm, const void* base, int C, int ld) -> int {
         unsigned long long dims[5], str[5];
@@ -164,7 +170,22 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
         r = encode_bf16_map(&tmW, a->weight, 2, dims, str, wbox);
         if (r != 0) return r;
     }
-    ddm::launch_conv(tmA0, tmA1, tmW, p, g_num_sms, as_stream(stream));
+    if (p.tma_store) {
+        unsigned long long dims[5], str[5];
+        const unsigned long long L = a->ld_out, OW = a->OW, OH = a->OH, B = a->B, W = a->W, H = a->H;
+        if (!strided_out) {           // [B,OH,OW,ld] -> (c, x, 1, y, b)
+            dims[0] = a->N; dims[1] = OW; dims[2] = 1; dims[3] = OH; dims[4] = B;
+            str[0] = 1; str[1] = L; str[2] = L * OW; str[3] = L * OW; str[4] = L * OW * OH;
+        } else {                      // [B,2H,2W,N] -> ((px c), x, py, y, b): one sub-pixel phase per launch
+            dims[0] = 2ull * L; dims[1] = W; dims[2] = 2; dims[3] = H; dims[4] = B;
+            str[0] = 1; str[1] = 2ull * L; str[2] = OW * L; str[3] = 2ull * OW * L; str[4] = OH * OW * L;
+        }
+        r = encode_bf16_map(&tmOut, a->out, 5, dims, str, box);
+        if (r != 0) return r;
+    } else {
+        tmOut = tmA0;
+    }
+    ddm::launch_conv(tmA0, tmA1, tmW, tmOut, p, g_num_sms, as_stream(stream));
     return finish(1);
 }
 

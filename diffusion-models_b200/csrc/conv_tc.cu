@@ -15,8 +15,14 @@ struct alignas(8) ConvBarriers {
     uint32_t pad;
 };
 
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+constexpr int kEpiThreads = 32 * kEpilogueWarps;   // 256
+constexpr int kBarPre = 1, kBarPost = 2;           // named barriers of the epilogue warps
 
+// SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2 : one MUFU op per element
+__device__ __forceinline__ float silu_f(float v) {
+    const float h = 0.5f * v;
+    return fmaf(h, tanh_approx(h), h);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -24,17 +30,42 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+struct SmemPlan {
+    int stage_bytes, staging_off, colp_off, red_off, bars_off, total;
+};
+__host__ __device__ inline SmemPlan make_plan(int block_n, int n_pad, int tma_store, int num_stages) {
+    SmemPlan s;
+    s.stage_bytes = kATileBytes + block_n * (kChunkK * 2);
+    s.staging_off = num_stages * s.stage_bytes;
+    s.colp_off = s.staging_off + (tma_store ? kTileM * block_n * 2 : 0);
+    s.red_off = s.colp_off + 3 * n_pad * 4;
+    s.bars_off = s.red_off + 4 * kTileM * 4;
+    s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
+    return s;
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ ConvParams p) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = kATileBytes + p.block_n * (kChunkK * 2);
-    ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(smem + p.num_stages * stage_bytes);
+    const SmemPlan plan = make_plan(p.block_n, p.n_pad, p.tma_store, p.num_stages);
+    const int stage_bytes = plan.stage_bytes;
+    uint8_t* staging = smem + plan.staging_off;
+    float* col_bias = reinterpret_cast<float*>(smem + plan.colp_off);
+    float* col_mul = col_bias + p.n_pad;
+    float* col_add = col_mul + p.n_pad;
+    float* red_a = reinterpret_cast<float*>(smem + plan.red_off);      // [2][128] partial sum of squares (pre-norm)
+    float* red_b = red_a + 2 * kTileM;                                 // [2][128] partial sum of squares (stored row)
+    ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(smem + plan.bars_off);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool ss_uniform = (p.scale_shift != nullptr) && (p.ss_stride == 0);
+    const bool ss_batched = (p.scale_shift != nullptr) && (p.ss_stride != 0);
+    const bool affine = (p.norm_g != nullptr) || ss_uniform;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
@@ -43,16 +74,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 1);
-            mbar_init(&bars->acc_empty[a], 128);
+            mbar_init(&bars->acc_empty[a], kEpiThreads);
         }
         fence_barrier_init();
         prefetch_tmap(&tmA0);
         prefetch_tmap(&tmA1);
         prefetch_tmap(&tmW);
+        prefetch_tmap(&tmOut);
     }
     if (warp == 1) {
         tmem_alloc(&bars->tmem_base, static_cast<uint32_t>(p.tmem_cols));
         tmem_relinquish();
+    }
+    // per-column epilogue vectors: v = acc*rs + bias ; [v *= rinv] ; v = v*mul + add
+    for (int n = threadIdx.x; n < p.n_pad; n += blockDim.x) {
+        const bool in = n < p.N;
+        float m = 1.0f, a = 0.0f;
+        if (in && p.norm_g != nullptr) m = __ldg(p.norm_g + n);
+        if (in && ss_uniform) {
+            m *= __ldg(p.scale_shift + n) + 1.0f;
+            a = __ldg(p.scale_shift + p.N + n);
+        }
+        col_bias[n] = (in && p.bias != nullptr) ? __ldg(p.bias + n) : 0.0f;
+        col_mul[n] = m;
+        col_add[n] = a;
     }
     tc_fence_before();
     __syncthreads();
@@ -126,12 +171,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        const int ew = warp - 2;
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int half = ew >> 2;               // column half handled by this warp
         const int r = q * 32 + lane;            // accumulator row == tile pixel
         const int bx = r % p.bw;
         const int by = (r / p.bw) % p.bh;
         const int bi = r / (p.bw * p.bh);
+        const bool store_leader = (ew == 0) && (lane == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -140,119 +188,175 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int tx = m_tile % p.tiles_x;
             const int ty = (m_tile / p.tiles_x) % p.tiles_y;
             const int tb = m_tile / (p.tiles_x * p.tiles_y);
-            const int x = tx * p.bw + bx, y = ty * p.bh + by, b = tb * p.bb + bi;
+            const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+            const int x = x0 + bx, y = y0 + by, b = b0 + bi;
             const int n0 = n_tile * p.block_n;
             const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
             const int oyy = y * p.sy + p.oy, oxx = x * p.sx + p.ox;
             const long long out_pix = (static_cast<long long>(b) * p.OH + oyy) * p.OW + oxx;
             const float rs = (p.row_scale != nullptr && valid)
                                  ? __ldg(p.row_scale + (static_cast<long long>(b) * p.H + y) * p.W + x) : 1.0f;
-            const float* ss = (p.scale_shift != nullptr) ? p.scale_shift + static_cast<long long>(valid ? b : 0) * p.ss_stride
-                                                         : nullptr;
+            const float* ssb = ss_batched ? p.scale_shift + static_cast<long long>(valid ? b : 0) * p.ss_stride : nullptr;
+
+            const int ncols = min(p.block_n, p.N - n0);
+            const int nchunks = (ncols + 15) >> 4;
+            const int c_mid = (nchunks + 1) >> 1;
+            const int c_lo = half == 0 ? 0 : c_mid;
+            const int c_hi = half == 0 ? c_mid : nchunks;
 
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.acc_stride);
-            const int ncols = min(p.block_n, p.N - n0);      // real columns of this N tile (multiple of 16 not required)
-            const int nchunks = (ncols + 15) >> 4;
 
-            float rinv = 1.0f;
             if (p.norm_g != nullptr) {
                 float sumsq = 0.0f;
-                for (int c = 0; c < nchunks; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
+                    __syncwarp();
                     uint32_t v[16];
                     tmem_ld16(t_row + c * 16, v);
                     tmem_ld_wait();
+                    const float4* b4 = reinterpret_cast<const float4*>(col_bias + n0 + c * 16);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + c * 16 + j;
-                        if (n < p.N) {
-                            float f = __uint_as_float(v[j]) * rs;
-                            if (p.bias != nullptr) f += __ldg(p.bias + n);
-                            sumsq = fmaf(f, f, sumsq);
-                        }
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 bb4 = b4[j4];
+                        const float f0 = fmaf(__uint_as_float(v[4 * j4 + 0]), rs, bb4.x);
+                        const float f1 = fmaf(__uint_as_float(v[4 * j4 + 1]), rs, bb4.y);
+                        const float f2 = fmaf(__uint_as_float(v[4 * j4 + 2]), rs, bb4.z);
+                        const float f3 = fmaf(__uint_as_float(v[4 * j4 + 3]), rs, bb4.w);
+                        sumsq = fmaf(f0, f0, sumsq);
+                        sumsq = fmaf(f1, f1, sumsq);
+                        sumsq = fmaf(f2, f2, sumsq);
+                        sumsq = fmaf(f3, f3, sumsq);      // padded columns have acc == 0 and bias == 0
                     }
                 }
-                rinv = 1.0f / fmaxf(sqrtf(sumsq), 1e-12f);
+                red_a[half * kTileM + r] = sumsq;
             }
+            // the previous tile's TMA stores must have finished reading the staging buffer before it is rewritten
+            if (p.tma_store && store_leader) bulk_wait_group_read<0>();
+            named_bar_sync(kBarPre, kEpiThreads);
+            float rinv = 1.0f;
+            if (p.norm_g != nullptr) rinv = 1.0f / fmaxf(sqrtf(red_a[r] + red_a[kTileM + r]), 1e-12f);
 
             float out_sumsq = 0.0f;
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
+                __syncwarp();
                 uint32_t v[16];
                 tmem_ld16(t_row + c * 16, v);
                 tmem_ld_wait();
-                if (c == nchunks - 1) {
+                if (c == c_hi - 1) {
                     // last TMEM read of this accumulator stage: hand it back to the MMA warp before the stores
                     tc_fence_before();
                     mbar_arrive(&bars->acc_empty[acc]);
                 }
                 float f[16];
                 const int nb = n0 + c * 16;
+                {
+                    const float4* b4 = reinterpret_cast<const float4*>(col_bias + nb);
+                    const float4* m4 = reinterpret_cast<const float4*>(col_mul + nb);
+                    const float4* a4 = reinterpret_cast<const float4*>(col_add + nb);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = nb + j;
-                    float t = 0.0f;
-                    if (n < p.N) {
-                        t = __uint_as_float(v[j]) * rs;
-                        if (p.bias != nullptr) t += __ldg(p.bias + n);
-                        if (p.norm_g != nullptr) t = t * rinv * __ldg(p.norm_g + n);
-                        if (ss != nullptr) t = fmaf(t, __ldg(ss + n) + 1.0f, __ldg(ss + p.N + n));
-                        if (p.act == 1) t = silu_f(t);
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 bb4 = b4[j4];
+                        f[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), rs, bb4.x);
+                        f[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), rs, bb4.y);
+                        f[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), rs, bb4.z);
+                        f[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), rs, bb4.w);
+                        if (affine) {
+                            const float4 mm = m4[j4], aa = a4[j4];
+                            f[4 * j4 + 0] = fmaf(f[4 * j4 + 0] * rinv, mm.x, aa.x);
+                            f[4 * j4 + 1] = fmaf(f[4 * j4 + 1] * rinv, mm.y, aa.y);
+                            f[4 * j4 + 2] = fmaf(f[4 * j4 + 2] * rinv, mm.z, aa.z);
+                            f[4 * j4 + 3] = fmaf(f[4 * j4 + 3] * rinv, mm.w, aa.w);
+                        }
                     }
-                    f[j] = t;
                 }
-                if (!valid) continue;
+                if (ssb != nullptr) {          // per-sample time embedding (generic forward, not the sampling loop)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (nb + j < p.N) f[j] = fmaf(f[j], __ldg(ssb + nb + j) + 1.0f, __ldg(ssb + p.N + nb + j));
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+                }
                 if (p.out_f32_nchw) {
-                    float* o = reinterpret_cast<float*>(p.out);
+                    if (valid) {
+                        float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = nb + j;
-                        if (n < p.N) o[((static_cast<long long>(b) * p.N + n) * p.OH + oyy) * p.OW + oxx] = f[j];
-                    }
-                } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.ld_out + nb;
-                    const bool full16 = (nb + 16 <= p.N);
-                    if (p.residual != nullptr) {
-                        const __nv_bfloat16* rp = p.residual + out_pix * p.ld_res + nb;
-                        if (full16) {
-                            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-                            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                f[2 * j] += bf16_lo(rr[j]);
-                                f[2 * j + 1] += bf16_hi(rr[j]);
-                            }
-                        } else {
-                            for (int j = 0; j < 16 && nb + j < p.N; ++j) f[j] += __bfloat162float(rp[j]);
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = nb + j;
+                            if (n < p.N) o[((static_cast<long long>(b) * p.N + n) * p.OH + oyy) * p.OW + oxx] = f[j];
                         }
                     }
+                    continue;
+                }
+                const bool full16 = (nb + 16 <= p.N);
+                if (p.residual != nullptr && valid) {
+                    const __nv_bfloat16* rp = p.residual + out_pix * p.ld_res + nb;
                     if (full16) {
-                        uint32_t w[8];
+                        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
+                        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                        if (p.rnorm_out != nullptr) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float a = bf16_lo(w[j]), c2 = bf16_hi(w[j]);
-                                out_sumsq = fmaf(a, a, fmaf(c2, c2, out_sumsq));
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            f[2 * j] += bf16_lo(rr[j]);
+                            f[2 * j + 1] += bf16_hi(rr[j]);
                         }
+                    } else {
+                        for (int j = 0; j < 16 && nb + j < p.N; ++j) f[j] += __bfloat162float(rp[j]);
+                    }
+                }
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                if (p.rnorm_out != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = bf16_lo(w[j]), c2 = bf16_hi(w[j]);
+                        out_sumsq = fmaf(a, a, fmaf(c2, c2, out_sumsq));   // padded columns are exactly 0
+                    }
+                }
+                if (p.tma_store) {
+                    // staging: [group of 64 channels][128 rows][128 B], 16-byte units XOR-swizzled by (row & 7)
+                    const int cl = c * 16;                       // column inside this N tile
+                    uint8_t* rowp = staging + (cl >> 6) * (kTileM * 128) + r * 128;
+                    const int u = (cl & 63) >> 3;                // 16-byte unit inside the 128-byte row
+                    *reinterpret_cast<uint4*>(rowp + (((u) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(rowp + (((u + 1) ^ (r & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                } else if (valid) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.ld_out + nb;
+                    if (full16) {
                         reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                         reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
                     } else {
-                        for (int j = 0; j < 16 && nb + j < p.N; ++j) {
-                            const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
-                            const float a = __bfloat162float(h);
-                            out_sumsq = fmaf(a, a, out_sumsq);
-                            o[j] = h;
-                        }
+                        for (int j = 0; j < 16 && nb + j < p.N; ++j) o[j] = __float2bfloat16_rn(f[j]);
                     }
                 }
             }
-            if (p.rnorm_out != nullptr && valid) p.rnorm_out[out_pix] = 1.0f / fmaxf(sqrtf(out_sumsq), 1e-12f);
+            if (c_lo >= c_hi) {               // a warp with no columns still owes its arrival
+                tc_fence_before();
+                mbar_arrive(&bars->acc_empty[acc]);
+            }
+            if (p.rnorm_out != nullptr) red_b[half * kTileM + r] = out_sumsq;
+            if (p.tma_store) fence_proxy_async();
+            named_bar_sync(kBarPost, kEpiThreads);
+            if (p.tma_store && store_leader) {
+                const int groups = (ncols + 63) >> 6;
+                for (int g = 0; g < groups; ++g) {
+                    const int ch = n0 + g * 64;
+                    if (p.sy == 2) {     // sub-pixel phase: output viewed as [B, H, (py), W, (px c)]
+                        tma_store_5d(&tmOut, staging + g * (kTileM * 128), p.ox * p.ld_out + ch, x0, p.oy, y0, b0);
+                    } else {
+                        tma_store_5d(&tmOut, staging + g * (kTileM * 128), ch, x0, 0, y0, b0);
+                    }
+                }
+                bulk_commit_group();
+            }
+            if (p.rnorm_out != nullptr && half == 0 && valid)
+                p.rnorm_out[out_pix] = 1.0f / fmaxf(sqrtf(red_b[r] + red_b[kTileM + r]), 1e-12f);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.tma_store && store_leader) bulk_wait_group<0>();
     }
 
     tc_fence_before();
@@ -265,19 +369,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
 }  // namespace
 
-int conv_smem_bytes(int block_n, int num_stages) {
-    return num_stages * (kATileBytes + block_n * kChunkK * 2) + static_cast<int>(sizeof(ConvBarriers)) + 1024;
+int conv_smem_plan(int block_n, int n_pad, int tma_store, int* num_stages) {
+    const int budget = 227 * 1024 - 1024;         // minus the alignment slack
+    int stages = 8;
+    while (stages > 2 && make_plan(block_n, n_pad, tma_store, stages).total > budget) --stages;
+    *num_stages = stages;
+    return make_plan(block_n, n_pad, tma_store, stages).total + 1024;
 }
 
 int conv_prepare_attributes() {
     return static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
-void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const ConvParams& p,
-                 int num_sms, cudaStream_t stream) {
+void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
+                 const ConvParams& p, int num_sms, cudaStream_t stream) {
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-    const int smem = conv_smem_bytes(p.block_n, p.num_stages);
-    conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(tmA0, tmA1, tmW, p);
+    int stages = 0;
+    const int smem = conv_smem_plan(p.block_n, p.n_pad, p.tma_store, &stages);
+    conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(tmA0, tmA1, tmW, tmOut, p);
 }
 
 }  // namespace ddm

@@ -6,8 +6,10 @@
 //   B tile (block_n x 64, bf16)             : 2-D TMA box of the packed weight matrix [N_pad][K_pad] (K contiguous).
 //   D (128 x block_n fp32)                  : TMEM accumulator, double buffered so the epilogue of tile i overlaps
 //     the main loop of tile i+1.
-// Warp roles: warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner, warps 2..5 = epilogue
-// (one thread per accumulator row == one output pixel, so the per-pixel RMSNorm over C_out is thread-local).
+// Warp roles: warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner, warps 2..9 = epilogue:
+// thread = (accumulator row, column half), so the per-pixel RMSNorm over C_out is two partial sums exchanged through
+// shared memory.  Per-column epilogue vectors (bias, norm gain x (scale+1), shift) are staged in shared memory once
+// per CTA; the bf16 output tile is staged in 128B-swizzled shared memory and written with TMA stores.
 //
 // Reference ops folded here (denoising_diffusion.py): Block.forward :113-122 (conv -> RMSNorm -> scale/shift -> SiLU),
 // ResnetBlock residual add :148, Downsample :54-58 (view 1), Upsample :48-52 (4 sub-pixel phases, strided output),
@@ -23,7 +25,9 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements per k-chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * kChunkK * 2; // 16 KiB
 constexpr int kMaxTaps = 9;
-constexpr int kConvThreads = 192;
+constexpr int kEpilogueWarps = 8;
+constexpr int kConvThreads = 64 + 32 * kEpilogueWarps;   // producer warp + MMA warp + epilogue warps
+constexpr int kMaxNPad = 512;
 
 struct ConvParams {
     // tile domain (pixel grid the taps are applied on) and tile box
@@ -32,12 +36,14 @@ struct ConvParams {
     int tiles_x, tiles_y, m_tiles, n_tiles, total_tiles;
     int block_n;                 // UMMA N: multiple of 16, <= 256
     int N;                       // real C_out
+    int n_pad;                   // N rounded up to 16
     int ntaps;
     int tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_p[kMaxTaps];
     int chunks0, chunks1;        // 64-channel chunks per tap for source 0 / source 1
     int acc_stride;              // TMEM columns between the two accumulator stages
     int tmem_cols;               // allocated TMEM columns (power of two >= 32)
     int num_stages;              // smem ring depth
+    int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)
     // epilogue
     const float* bias;           // [N] or null
     const float* row_scale;      // [B*H*W] or null : v = acc * row_scale[pixel]
@@ -54,9 +60,10 @@ struct ConvParams {
     float* rnorm_out;            // [B*OH*OW] or null : 1/max(||out_row||_2, 1e-12) of the stored row
 };
 
-void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const ConvParams& p,
-                 int num_sms, cudaStream_t stream);
-int conv_smem_bytes(int block_n, int num_stages);
+void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
+                 const ConvParams& p, int num_sms, cudaStream_t stream);
+// shared-memory plan: returns total dynamic bytes and the stage count that fits
+int conv_smem_plan(int block_n, int n_pad, int tma_store, int* num_stages);
 int conv_prepare_attributes();
 
 }  // namespace ddm
