@@ -117,12 +117,47 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.N = a->N;
     if (a->norm_g != nullptr && p.n_tiles != 1) return DDM_E_UNSUPPORTED;
     if (a->rnorm_out != nullptr && (p.n_tiles != 1 || a->out_f32_nchw)) return DDM_E_UNSUPPORTED;
-    p.ntaps = a->ntaps;
-    for (int t = 0; t < a->ntaps; ++t) { p.tap_dy[t] = a->tap_dy[t]; p.tap_dx[t] = a->tap_dx[t]; p.tap_p[t] = a->tap_p[t]; }
+    // group taps into slabs (same dx and p, consecutive dy) when the dy shift is expressible as an aligned row offset
+    auto set_slabs = [&](bool want_group) {
+        bool can_group = want_group && (p.bb == 1) && (p.bw % 8 == 0);
+        int gdx[DDM_MAX_TAPS], gp[DDM_MAX_TAPS], gcnt[DDM_MAX_TAPS], gdy[DDM_MAX_TAPS][DDM_MAX_TAPS], gtap[DDM_MAX_TAPS][DDM_MAX_TAPS];
+        int ng = 0;
+        for (int t = 0; t < a->ntaps && can_group; ++t) {
+            int g = 0;
+            while (g < ng && !(gdx[g] == a->tap_dx[t] && gp[g] == a->tap_p[t])) ++g;
+            if (g == ng) { gdx[g] = a->tap_dx[t]; gp[g] = a->tap_p[t]; gcnt[g] = 0; ++ng; }
+            gdy[g][gcnt[g]] = a->tap_dy[t]; gtap[g][gcnt[g]] = t; ++gcnt[g];
+        }
+        for (int g = 0; g < ng && can_group; ++g) {
+            if (gcnt[g] != gcnt[0] || gcnt[g] > 3) can_group = false;
+            for (int j = 0; j < gcnt[g] && can_group; ++j) {     // insertion sort by dy, then require consecutive dy
+                for (int i = j; i > 0 && gdy[g][i] < gdy[g][i - 1]; --i) {
+                    int tdy = gdy[g][i]; gdy[g][i] = gdy[g][i - 1]; gdy[g][i - 1] = tdy;
+                    int tt = gtap[g][i]; gtap[g][i] = gtap[g][i - 1]; gtap[g][i - 1] = tt;
+                }
+            }
+            for (int j = 1; j < gcnt[g] && can_group; ++j) if (gdy[g][j] != gdy[g][j - 1] + 1) can_group = false;
+        }
+        if (can_group && ng > 0 && gcnt[0] > 1) {
+            p.n_slabs = ng; p.n_dy = gcnt[0];
+            for (int g = 0; g < ng; ++g) {
+                p.slab_dx[g] = gdx[g]; p.slab_p[g] = gp[g]; p.slab_dy0[g] = gdy[g][0];
+                for (int j = 0; j < p.n_dy; ++j) p.slab_tap[g][j] = gtap[g][j];
+            }
+        } else {
+            p.n_slabs = a->ntaps; p.n_dy = 1;
+            for (int t = 0; t < a->ntaps; ++t) {
+                p.slab_dx[t] = a->tap_dx[t]; p.slab_p[t] = a->tap_p[t]; p.slab_dy0[t] = a->tap_dy[t]; p.slab_tap[t][0] = t;
+            }
+        }
+        p.a_rows = p.bw * (p.bh + p.n_dy - 1) * p.bb;
+        return p.n_dy > 1;
+    };
     const int ceff0 = a->view == 1 ? 2 * a->C0 : a->C0;
     p.chunks0 = (ceff0 + 63) / 64;
     p.chunks1 = a->src1 != nullptr ? (a->C1 + 63) / 64 : 0;
     if (a->ntaps * (p.chunks0 + p.chunks1) * 64 != a->K_pad) return DDM_E_BAD_ARGUMENT;
+    p.k_chunks = a->ntaps * (p.chunks0 + p.chunks1);
     p.tmem_cols = pow2_ceil(2 * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
     p.acc_stride = p.tmem_cols / 2;
     p.n_pad = a->N_pad;
@@ -132,7 +167,20 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if (strided_out && !(a->sy == 2 && a->sx == 2 && a->OH == 2 * a->H && a->OW == 2 * a->W)) return DDM_E_UNSUPPORTED;
     p.tma_store = (!a->out_f32_nchw && (a->N % 64) == 0 && (!strided_out || a->ld_out == a->N) && a->OH >= a->H * a->sy &&
                    a->OW >= a->W * a->sx) ? 1 : 0;
-    ddm::conv_smem_plan(p.block_n, p.n_pad, p.tma_store, &p.num_stages);
+    // shared-memory configuration: prefer A-slab reuse and resident weights, as long as >= 3 pipeline stages remain
+    {
+        bool done = false;
+        for (int grouped = 1; grouped >= 0 && !done; --grouped) {
+            if (grouped && !set_slabs(true)) continue;
+            if (!grouped) set_slabs(false);
+            for (int resident = (p.n_tiles == 1 ? 1 : 0); resident >= 0 && !done; --resident) {
+                p.b_resident = resident;
+                ddm::conv_smem_plan(p, &p.num_stages);
+                if (p.num_stages >= (grouped || resident ? 3 : 2)) done = true;
+            }
+        }
+        if (!done) return DDM_E_UNSUPPORTED;
+    }
     p.bias = a->bias; p.row_scale = a->row_scale; p.norm_g = a->norm_g; p.scale_shift = a->scale_shift;
     p.ss_stride = a->ss_stride; p.act = a->act;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ld_res = a->ld_res;
@@ -142,6 +190,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
 
     CUtensorMap tmA0, tmA1, tmW, tmOut;
     const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};
+    const unsigned abox[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh + p.n_dy - 1), static_cast<unsigned>(p.bb)};
     auto encode_src = [&](CUtensorMap* tm, const void* base, int C, int ld) -> int {
         unsigned long long dims[5], str[5];
         const unsigned long long W = a->W, H = a->H, B = a->B, L = ld;
@@ -153,7 +202,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             dims[0] = 2ull * C; dims[1] = W; dims[2] = 2; dims[3] = H; dims[4] = B;
             str[0] = 1; str[1] = 2ull * L; str[2] = 2ull * W * L; str[3] = 4ull * W * L; str[4] = 4ull * W * H * L;
         }
-        return encode_bf16_map(tm, base, 5, dims, str, box);
+        return encode_bf16_map(tm, base, 5, dims, str, abox);
     };
     int r = encode_src(&tmA0, a->src0, a->C0, a->ld0);
     if (r != 0) return r;

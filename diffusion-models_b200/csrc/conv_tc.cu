@@ -11,6 +11,7 @@ struct alignas(8) ConvBarriers {
     uint64_t empty[8];
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
+    uint64_t w_full;
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -31,14 +32,17 @@ __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 struct SmemPlan {
-    int stage_bytes, staging_off, colp_off, red_off, bars_off, total;
+    int a_bytes, b_chunk_bytes, stage_bytes, wres_off, staging_off, colp_off, red_off, bars_off, total;
 };
-__host__ __device__ inline SmemPlan make_plan(int block_n, int n_pad, int tma_store, int num_stages) {
+__host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stages) {
     SmemPlan s;
-    s.stage_bytes = kATileBytes + block_n * (kChunkK * 2);
-    s.staging_off = num_stages * s.stage_bytes;
-    s.colp_off = s.staging_off + (tma_store ? kTileM * block_n * 2 : 0);
-    s.red_off = s.colp_off + 3 * n_pad * 4;
+    s.a_bytes = p.a_rows * (kChunkK * 2);
+    s.b_chunk_bytes = p.block_n * (kChunkK * 2);
+    s.stage_bytes = s.a_bytes + (p.b_resident ? 0 : p.n_dy * s.b_chunk_bytes);
+    s.wres_off = num_stages * s.stage_bytes;
+    s.staging_off = s.wres_off + (p.b_resident ? p.k_chunks * s.b_chunk_bytes : 0);
+    s.colp_off = s.staging_off + (p.tma_store ? kTileM * p.block_n * 2 : 0);
+    s.red_off = s.colp_off + 3 * p.n_pad * 4;
     s.bars_off = s.red_off + 4 * kTileM * 4;
     s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
     return s;
@@ -51,8 +55,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const SmemPlan plan = make_plan(p.block_n, p.n_pad, p.tma_store, p.num_stages);
+    const SmemPlan plan = make_plan(p, p.num_stages);
     const int stage_bytes = plan.stage_bytes;
+    uint8_t* wres = smem + plan.wres_off;
     uint8_t* staging = smem + plan.staging_off;
     float* col_bias = reinterpret_cast<float*>(smem + plan.colp_off);
     float* col_mul = col_bias + p.n_pad;
@@ -76,6 +81,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_init(&bars->acc_full[a], 1);
             mbar_init(&bars->acc_empty[a], kEpiThreads);
         }
+        mbar_init(&bars->w_full, 1);
         fence_barrier_init();
         prefetch_tmap(&tmA0);
         prefetch_tmap(&tmA1);
@@ -105,11 +111,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t tmem_base = bars->tmem_base;
 
     const int chunks_per_tap = p.chunks0 + p.chunks1;
-    const int k_chunks = p.ntaps * chunks_per_tap;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
+            if (p.b_resident) {       // the weights of this (single) N tile are loaded once per CTA
+                mbar_arrive_expect_tx(&bars->w_full, static_cast<uint32_t>(p.k_chunks * plan.b_chunk_bytes));
+                for (int kc = 0; kc < p.k_chunks; ++kc)
+                    tma_load_2d(wres + kc * plan.b_chunk_bytes, &tmW, &bars->w_full, kc * kChunkK, 0);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -120,21 +130,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int tb = m_tile / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
                 const int n0 = n_tile * p.block_n;
-                int kcol = 0;
-                for (int t = 0; t < p.ntaps; ++t) {
-                    const int cx = x0 + p.tap_dx[t], cy = y0 + p.tap_dy[t], cp = p.tap_p[t];
+                for (int s = 0; s < p.n_slabs; ++s) {
+                    const int cx = x0 + p.slab_dx[s], cy = y0 + p.slab_dy0[s], cp = p.slab_p[s];
                     for (int c = 0; c < chunks_per_tap; ++c) {
                         mbar_wait(&bars->empty[stage], phase ^ 1u);
                         uint8_t* a_dst = smem + stage * stage_bytes;
-                        uint8_t* b_dst = a_dst + kATileBytes;
                         mbar_arrive_expect_tx(&bars->full[stage], static_cast<uint32_t>(stage_bytes));
                         if (c < p.chunks0) {
                             tma_load_5d(a_dst, &tmA0, &bars->full[stage], c * kChunkK, cx, cp, cy, b0);
                         } else {
                             tma_load_5d(a_dst, &tmA1, &bars->full[stage], (c - p.chunks0) * kChunkK, cx, cp, cy, b0);
                         }
-                        tma_load_2d(b_dst, &tmW, &bars->full[stage], kcol, n0);
-                        kcol += kChunkK;
+                        if (!p.b_resident) {
+                            for (int j = 0; j < p.n_dy; ++j)
+                                tma_load_2d(a_dst + plan.a_bytes + j * plan.b_chunk_bytes, &tmW, &bars->full[stage],
+                                            (p.slab_tap[s][j] * chunks_per_tap + c) * kChunkK, n0);
+                        }
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -148,23 +159,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            if (p.b_resident) mbar_wait(&bars->w_full, 0);
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
-                for (int kc = 0; kc < k_chunks; ++kc) {
-                    mbar_wait(&bars->full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-                    const uint64_t a_desc = umma_desc_sw128(a_addr);
-                    const uint64_t b_desc = umma_desc_sw128(a_addr + kATileBytes);
+                uint32_t accumulate = 0;
+                for (int s = 0; s < p.n_slabs; ++s) {
+                    for (int c = 0; c < chunks_per_tap; ++c) {
+                        mbar_wait(&bars->full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+                        for (int j = 0; j < p.n_dy; ++j) {
+                            // dy shift = j image rows = j * bw pixels = j * bw * 128 bytes (1024B-aligned) into the slab
+                            const uint64_t a_desc = umma_desc_sw128(a_addr + j * p.bw * (kChunkK * 2));
+                            const uint32_t b_addr = p.b_resident
+                                ? smem_u32(wres) + (p.slab_tap[s][j] * chunks_per_tap + c) * plan.b_chunk_bytes
+                                : a_addr + plan.a_bytes + j * plan.b_chunk_bytes;
+                            const uint64_t b_desc = umma_desc_sw128(b_addr);
 #pragma unroll
-                    for (int k = 0; k < kChunkK / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-                        umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < kChunkK / 16; ++k) {
+                                // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+                                umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
+                                accumulate = 1u;
+                            }
+                        }
+                        umma_commit(&bars->empty[stage]);
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
-                    umma_commit(&bars->empty[stage]);
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&bars->acc_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -369,12 +391,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
 }  // namespace
 
-int conv_smem_plan(int block_n, int n_pad, int tma_store, int* num_stages) {
+int conv_smem_plan(const ConvParams& p, int* num_stages) {
     const int budget = 227 * 1024 - 1024;         // minus the alignment slack
     int stages = 8;
-    while (stages > 2 && make_plan(block_n, n_pad, tma_store, stages).total > budget) --stages;
+    while (stages > 0 && make_plan(p, stages).total > budget) --stages;
     *num_stages = stages;
-    return make_plan(block_n, n_pad, tma_store, stages).total + 1024;
+    return make_plan(p, stages > 0 ? stages : 1).total + 1024;
 }
 
 int conv_prepare_attributes() {
@@ -385,7 +407,7 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
                  const ConvParams& p, int num_sms, cudaStream_t stream) {
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     int stages = 0;
-    const int smem = conv_smem_plan(p.block_n, p.n_pad, p.tma_store, &stages);
+    const int smem = conv_smem_plan(p, &stages);
     conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(tmA0, tmA1, tmW, tmOut, p);
 }
 

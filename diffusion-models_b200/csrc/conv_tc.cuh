@@ -37,8 +37,15 @@ struct ConvParams {
     int block_n;                 // UMMA N: multiple of 16, <= 256
     int N;                       // real C_out
     int n_pad;                   // N rounded up to 16
-    int ntaps;
-    int tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_p[kMaxTaps];
+    // taps grouped into "slabs": taps that share (dx, p) and have consecutive dy read one A slab of bh + n_dy - 1
+    // image rows; the dy shift is a 1024B-aligned row offset into the slab (needs bb == 1 and bw % 8 == 0, otherwise
+    // n_dy = 1 and every tap is its own slab).  slab_tap = position of the tap in the weight matrix's K order.
+    int n_slabs, n_dy;
+    int slab_dx[kMaxTaps], slab_p[kMaxTaps], slab_dy0[kMaxTaps];
+    int slab_tap[kMaxTaps][3];
+    int a_rows;                  // rows (pixels) of one A stage
+    int b_resident;              // 1: the whole weight matrix stays in shared memory for the CTA's lifetime
+    int k_chunks;                // taps x 64-channel chunks
     int chunks0, chunks1;        // 64-channel chunks per tap for source 0 / source 1
     int acc_stride;              // TMEM columns between the two accumulator stages
     int tmem_cols;               // allocated TMEM columns (power of two >= 32)
@@ -62,8 +69,8 @@ struct ConvParams {
 
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
                  const ConvParams& p, int num_sms, cudaStream_t stream);
-// shared-memory plan: returns total dynamic bytes and the stage count that fits
-int conv_smem_plan(int block_n, int n_pad, int tma_store, int* num_stages);
+// shared-memory plan: returns total dynamic bytes and the stage count that fits (0 stages = does not fit)
+int conv_smem_plan(const ConvParams& p, int* num_stages);
 int conv_prepare_attributes();
 
 }  // namespace ddm
