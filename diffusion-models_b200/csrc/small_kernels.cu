@@ -277,7 +277,9 @@ sampler_step_kernel(int kind, float* __restrict__ x, const float* __restrict__ m
     if (i0 >= numel) return;
     const float noise_amp = k4;                       // sigma (DDIM) or exp(0.5 logvar) (DDPM; 0 at t == 0)
     float z[4] = {0.f, 0.f, 0.f, 0.f};
-    if (noise_amp != 0.0f && noise == nullptr) normal4(seed, static_cast<unsigned long long>(step) + 1ull, static_cast<unsigned long long>(grp), z);
+    if (noise_amp != 0.0f && noise == nullptr)   // stream id = (call epoch, step): a replayed graph draws fresh noise every call
+        normal4(seed, (static_cast<unsigned long long>(static_cast<unsigned>(step_counter[1])) << 32) | (static_cast<unsigned long long>(step) + 1ull),
+                static_cast<unsigned long long>(grp), z);
     for (int j = 0; j < 4 && i0 + j < numel; ++j) {
         const long long i = i0 + j;
         const float xt = x[i], o = mo[i];

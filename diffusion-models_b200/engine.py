@@ -50,6 +50,7 @@ class UnetEngine:
         self.time_ops: List[Tuple[str, Callable[[int], int]]] = []
         self.text_ops: List[Tuple[str, Callable[[int], int]]] = []
         self.taps: Dict[str, torch.Tensor] = {}  # named activations for per-layer parity tests
+        self.loops: Dict[tuple, dict] = {}       # cached sampling loops (tables + captured step graph), see diffusion.py
         self._w = {k: v.detach() for k, v in weights.items()}
         self._build()
 

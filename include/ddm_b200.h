@@ -134,8 +134,9 @@ int ddm_attention(const void* q, int ldq, const void* k, int ldk, const void* v,
  * K9: per-timestep sampler update, one fused elementwise kernel (dd:603-626 model_predictions, dd:684-701 DDIM,
  * dd:628-645 + dd:594-601 ancestral DDPM).  State tensors are fp32 NCHW with `numel` elements.  The per-step
  * coefficients live in a device table so that one captured CUDA graph can be replayed for every step:
- * row s of `coef` (8 floats) is selected by *step_counter (device int32), which the kernel increments when
- * `advance` != 0.
+ * row s of `coef` (8 floats) is selected by step_counter[0] (device int32[2] = {step, call epoch}), which the kernel
+ * increments when `advance` != 0; step_counter[1] only salts the in-kernel noise stream so that replaying the same graph
+ * for a new sampling call draws new noise.
  *   DDIM row : { sqrt_recip_acp[t], sqrt_recipm1_acp[t], sqrt(acp[t_next]), c, sigma, is_last, sqrt_acp[t], sqrt_1m_acp[t] }
  *   DDPM row : { sqrt_recip_acp[t], sqrt_recipm1_acp[t], coef1[t], coef2[t], exp(0.5 logvar[t]) or 0 at t=0, 0,
  *                sqrt_acp[t], sqrt_1m_acp[t] }
