@@ -111,6 +111,11 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.tiles_y = (a->H + p.bh - 1) / p.bh;
     const int tiles_b = (a->B + p.bb - 1) / p.bb;
     p.m_tiles = p.tiles_x * p.tiles_y * tiles_b;
+    auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+    p.bw_shift = ilog2(p.bw); p.bh_shift = ilog2(p.bh);
+    p.tx_shift = ilog2(p.tiles_x); p.ty_shift = ilog2(p.tiles_y);
+    p.tiles_pow2 = ((1 << p.tx_shift) == p.tiles_x && (1 << p.ty_shift) == p.tiles_y) ? 1 : 0;
+    if (a->N_pad > 512) return DDM_E_UNSUPPORTED;
     p.n_tiles = (a->N_pad + 255) / 256;
     p.block_n = ((a->N_pad + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;   // e.g. N=384 -> 2 tiles of 192
     p.total_tiles = p.m_tiles * p.n_tiles;

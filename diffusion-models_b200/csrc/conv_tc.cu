@@ -16,7 +16,8 @@ struct alignas(8) ConvBarriers {
     uint32_t pad;
 };
 
-constexpr int kEpiThreads = 32 * kEpilogueWarps;   // 256
+constexpr int kEpiThreads = 32 * kEpilogueWarps;   // 512
+constexpr int kParts = kEpilogueWarps / 4;         // column parts per accumulator row
 constexpr int kBarPre = 1, kBarPost = 2;           // named barriers of the epilogue warps
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2 : one MUFU op per element
@@ -43,7 +44,7 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
     s.staging_off = s.wres_off + (p.b_resident ? p.k_chunks * s.b_chunk_bytes : 0);
     s.colp_off = s.staging_off + (p.tma_store ? kTileM * p.block_n * 2 : 0);
     s.red_off = s.colp_off + 3 * p.n_pad * 4;
-    s.bars_off = s.red_off + 4 * kTileM * 4;
+    s.bars_off = s.red_off + 2 * kParts * kTileM * 4;
     s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
     return s;
 }
@@ -62,8 +63,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     float* col_bias = reinterpret_cast<float*>(smem + plan.colp_off);
     float* col_mul = col_bias + p.n_pad;
     float* col_add = col_mul + p.n_pad;
-    float* red_a = reinterpret_cast<float*>(smem + plan.red_off);      // [2][128] partial sum of squares (pre-norm)
-    float* red_b = red_a + 2 * kTileM;                                 // [2][128] partial sum of squares (stored row)
+    float* red_a = reinterpret_cast<float*>(smem + plan.red_off);      // [parts][128] partial sum of squares (pre-norm)
+    float* red_b = red_a + kParts * kTileM;                            // [parts][128] partial sum of squares (stored row)
     ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(smem + plan.bars_off);
 
     const int warp = threadIdx.x >> 5;
@@ -193,23 +194,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // ------------------------------------------------------------------ epilogue (warps 2..17)
+        // thread = (accumulator row r, column part): 4 parts x 128 rows.  Two passes over TMEM when RMSNorm is on
+        // (sum of squares, then normalise); partial sums of the 4 parts meet in shared memory.
         const int ew = warp - 2;
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = ew >> 2;               // column half handled by this warp
+        const int part = ew >> 2;               // column part handled by this warp
         const int r = q * 32 + lane;            // accumulator row == tile pixel
-        const int bx = r % p.bw;
-        const int by = (r / p.bw) % p.bh;
-        const int bi = r / (p.bw * p.bh);
+        const int bx = r & (p.bw - 1);          // bw, bh are powers of two
+        const int by = (r >> p.bw_shift) & (p.bh - 1);
+        const int bi = r >> (p.bw_shift + p.bh_shift);
         const bool store_leader = (ew == 0) && (lane == 0);
+        const int tiles_xy = p.tiles_x * p.tiles_y;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int n_tile = tile / p.m_tiles;
+            const int n_tile = tile >= p.m_tiles ? 1 : 0;          // at most two N tiles (N <= 512)
             const int m_tile = tile - n_tile * p.m_tiles;
-            const int tx = m_tile % p.tiles_x;
-            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-            const int tb = m_tile / (p.tiles_x * p.tiles_y);
+            int tx, ty, tb;
+            if (p.tiles_pow2) {
+                tx = m_tile & (p.tiles_x - 1);
+                ty = (m_tile >> p.tx_shift) & (p.tiles_y - 1);
+                tb = m_tile >> (p.tx_shift + p.ty_shift);
+            } else {
+                tb = m_tile / tiles_xy;
+                const int rem = m_tile - tb * tiles_xy;
+                ty = rem / p.tiles_x;
+                tx = rem - ty * p.tiles_x;
+            }
             const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
             const int x = x0 + bx, y = y0 + by, b = b0 + bi;
             const int n0 = n_tile * p.block_n;
@@ -222,16 +234,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
             const int ncols = min(p.block_n, p.N - n0);
             const int nchunks = (ncols + 15) >> 4;
-            const int c_mid = (nchunks + 1) >> 1;
-            const int c_lo = half == 0 ? 0 : c_mid;
-            const int c_hi = half == 0 ? c_mid : nchunks;
+            const int per = (nchunks + kParts - 1) / kParts;
+            const int c_lo = min(nchunks, part * per);
+            const int c_hi = min(nchunks, c_lo + per);
+
+            // residual rows are fetched before waiting for the accumulator so that their latency hides behind the MMA
+            uint4 rpre[2][2];
+            const bool res_vec = (p.residual != nullptr) && valid && ((p.N & 15) == 0);
+            const __nv_bfloat16* rrow = p.residual != nullptr ? p.residual + out_pix * p.ld_res + n0 : nullptr;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (res_vec && c_lo + i < c_hi) {
+                    rpre[i][0] = __ldg(reinterpret_cast<const uint4*>(rrow + (c_lo + i) * 16));
+                    rpre[i][1] = __ldg(reinterpret_cast<const uint4*>(rrow + (c_lo + i) * 16) + 1);
+                }
+            }
 
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.acc_stride);
 
             if (p.norm_g != nullptr) {
-                float sumsq = 0.0f;
+                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
                 for (int c = c_lo; c < c_hi; ++c) {
                     __syncwarp();
                     uint32_t v[16];
@@ -245,19 +269,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         const float f1 = fmaf(__uint_as_float(v[4 * j4 + 1]), rs, bb4.y);
                         const float f2 = fmaf(__uint_as_float(v[4 * j4 + 2]), rs, bb4.z);
                         const float f3 = fmaf(__uint_as_float(v[4 * j4 + 3]), rs, bb4.w);
-                        sumsq = fmaf(f0, f0, sumsq);
-                        sumsq = fmaf(f1, f1, sumsq);
-                        sumsq = fmaf(f2, f2, sumsq);
-                        sumsq = fmaf(f3, f3, sumsq);      // padded columns have acc == 0 and bias == 0
+                        s0 = fmaf(f0, f0, s0);
+                        s1 = fmaf(f1, f1, s1);
+                        s2 = fmaf(f2, f2, s2);
+                        s3 = fmaf(f3, f3, s3);          // padded columns have acc == 0 and bias == 0
                     }
                 }
-                red_a[half * kTileM + r] = sumsq;
+                red_a[part * kTileM + r] = (s0 + s1) + (s2 + s3);
             }
             // the previous tile's TMA stores must have finished reading the staging buffer before it is rewritten
             if (p.tma_store && store_leader) bulk_wait_group_read<0>();
             named_bar_sync(kBarPre, kEpiThreads);
             float rinv = 1.0f;
-            if (p.norm_g != nullptr) rinv = 1.0f / fmaxf(sqrtf(red_a[r] + red_a[kTileM + r]), 1e-12f);
+            if (p.norm_g != nullptr)
+                rinv = 1.0f / fmaxf(sqrtf((red_a[r] + red_a[kTileM + r]) + (red_a[2 * kTileM + r] + red_a[3 * kTileM + r])), 1e-12f);
 
             float out_sumsq = 0.0f;
             for (int c = c_lo; c < c_hi; ++c) {
@@ -312,20 +337,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     continue;
                 }
-                const bool full16 = (nb + 16 <= p.N);
                 if (p.residual != nullptr && valid) {
-                    const __nv_bfloat16* rp = p.residual + out_pix * p.ld_res + nb;
-                    if (full16) {
-                        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-                        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            f[2 * j] += bf16_lo(rr[j]);
-                            f[2 * j + 1] += bf16_hi(rr[j]);
+                    if (res_vec) {
+                        uint4 r0, r1;
+                        const int i = c - c_lo;
+                        if (i == 0) { r0 = rpre[0][0]; r1 = rpre[0][1]; }
+                        else if (i == 1) { r0 = rpre[1][0]; r1 = rpre[1][1]; }
+                        else {
+                            r0 = __ldg(reinterpret_cast<const uint4*>(rrow + c * 16));
+                            r1 = __ldg(reinterpret_cast<const uint4*>(rrow + c * 16) + 1);
                         }
+                        f[0] += bf16_lo(r0.x); f[1] += bf16_hi(r0.x); f[2] += bf16_lo(r0.y); f[3] += bf16_hi(r0.y);
+                        f[4] += bf16_lo(r0.z); f[5] += bf16_hi(r0.z); f[6] += bf16_lo(r0.w); f[7] += bf16_hi(r0.w);
+                        f[8] += bf16_lo(r1.x); f[9] += bf16_hi(r1.x); f[10] += bf16_lo(r1.y); f[11] += bf16_hi(r1.y);
+                        f[12] += bf16_lo(r1.z); f[13] += bf16_hi(r1.z); f[14] += bf16_lo(r1.w); f[15] += bf16_hi(r1.w);
                     } else {
-                        for (int j = 0; j < 16 && nb + j < p.N; ++j) f[j] += __bfloat162float(rp[j]);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nb + j < p.N) f[j] += __bfloat162float(rrow[c * 16 + j]);
                     }
                 }
                 uint32_t w[8];
@@ -347,11 +376,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     *reinterpret_cast<uint4*>(rowp + (((u + 1) ^ (r & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
                 } else if (valid) {
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.ld_out + nb;
-                    if (full16) {
+                    if (nb + 16 <= p.N) {
                         reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                         reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
                     } else {
-                        for (int j = 0; j < 16 && nb + j < p.N; ++j) o[j] = __float2bfloat16_rn(f[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (nb + 2 * j < p.N) o[2 * j] = __ushort_as_bfloat16(static_cast<unsigned short>(w[j] & 0xFFFFu));
+                            if (nb + 2 * j + 1 < p.N) o[2 * j + 1] = __ushort_as_bfloat16(static_cast<unsigned short>(w[j] >> 16));
+                        }
                     }
                 }
             }
@@ -359,7 +392,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 tc_fence_before();
                 mbar_arrive(&bars->acc_empty[acc]);
             }
-            if (p.rnorm_out != nullptr) red_b[half * kTileM + r] = out_sumsq;
+            if (p.rnorm_out != nullptr) red_b[part * kTileM + r] = out_sumsq;
             if (p.tma_store) fence_proxy_async();
             named_bar_sync(kBarPost, kEpiThreads);
             if (p.tma_store && store_leader) {
@@ -374,8 +407,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 bulk_commit_group();
             }
-            if (p.rnorm_out != nullptr && half == 0 && valid)
-                p.rnorm_out[out_pix] = 1.0f / fmaxf(sqrtf(red_b[r] + red_b[kTileM + r]), 1e-12f);
+            if (p.rnorm_out != nullptr && part == 0 && valid)
+                p.rnorm_out[out_pix] =
+                    1.0f / fmaxf(sqrtf((red_b[r] + red_b[kTileM + r]) + (red_b[2 * kTileM + r] + red_b[3 * kTileM + r])), 1e-12f);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (p.tma_store && store_leader) bulk_wait_group<0>();

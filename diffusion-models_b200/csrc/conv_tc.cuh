@@ -6,8 +6,8 @@
 //   B tile (block_n x 64, bf16)             : 2-D TMA box of the packed weight matrix [N_pad][K_pad] (K contiguous).
 //   D (128 x block_n fp32)                  : TMEM accumulator, double buffered so the epilogue of tile i overlaps
 //     the main loop of tile i+1.
-// Warp roles: warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner, warps 2..9 = epilogue:
-// thread = (accumulator row, column half), so the per-pixel RMSNorm over C_out is two partial sums exchanged through
+// Warp roles: warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner, warps 2..17 = epilogue:
+// thread = (accumulator row, column part), so the per-pixel RMSNorm over C_out is four partial sums exchanged through
 // shared memory.  Per-column epilogue vectors (bias, norm gain x (scale+1), shift) are staged in shared memory once
 // per CTA; the bf16 output tile is staged in 128B-swizzled shared memory and written with TMA stores.
 //
@@ -25,7 +25,7 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements per k-chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * kChunkK * 2; // 16 KiB
 constexpr int kMaxTaps = 9;
-constexpr int kEpilogueWarps = 8;
+constexpr int kEpilogueWarps = 16;
 constexpr int kConvThreads = 64 + 32 * kEpilogueWarps;   // producer warp + MMA warp + epilogue warps
 constexpr int kMaxNPad = 512;
 
@@ -34,6 +34,8 @@ struct ConvParams {
     int B, H, W;
     int bw, bh, bb;
     int tiles_x, tiles_y, m_tiles, n_tiles, total_tiles;
+    int bw_shift, bh_shift;      // log2 of bw, bh
+    int tiles_pow2, tx_shift, ty_shift;   // tiles_x and tiles_y both powers of two -> shift/mask tile decode
     int block_n;                 // UMMA N: multiple of 16, <= 256
     int N;                       // real C_out
     int n_pad;                   // N rounded up to 16
