@@ -272,7 +272,7 @@ int launch_linear_attention(const void* qkv, const float* mem_kv, void* out, int
     auto* o = reinterpret_cast<__nv_bfloat16*>(out);
     switch (d) {
         case 16: linear_attention_kernel<16><<<grid, 256, 0, s>>>(q, mem_kv, o, n, heads, n_mem); return 0;
-        case 32: linear_attention_kernel<32><<<grid, 256, 0, s>>>(q, mem_kv, o, n, heads, n_mem); return 0;
+        case 32: launch_linattn32_tc(qkv, mem_kv, out, B, n, heads, n_mem, s); return 0;   // tensor-core path
         case 64: linear_attention_kernel<64><<<grid, 256, 0, s>>>(q, mem_kv, o, n, heads, n_mem); return 0;
         default: return -3;
     }

@@ -24,6 +24,9 @@ void launch_finalize(const float* x, float* y, int unnorm, long long numel, cuda
 void launch_select_row(const float* table, const int* step_counter, float* dst, int row_len, cudaStream_t s);
 void launch_randn(float* x, unsigned long long seed, unsigned long long sid, long long numel, cudaStream_t s);
 
+// linattn_tc.cu
+void launch_linattn32_tc(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int n_mem, cudaStream_t s);
+
 // attention.cu
 int attention_prepare_attributes();
 int launch_linear_attention(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int d, int n_mem, cudaStream_t s);
