@@ -84,6 +84,8 @@ int ddm_init(int device) {
     if (r != 0) return r;
     r = ddm::stem_prepare_attributes();
     if (r != 0) return r;
+    r = ddm::stem_tc_prepare_attributes();
+    if (r != 0) return r;
     g_ready = true;
     return 0;
 }
@@ -247,8 +249,13 @@ int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const floa
                   const float* bias, void* out_bf16, int B, int H, int W, int Cout, int ksize, void* stream) {
     if (!g_ready) return DDM_E_NOT_INITIALISED;
     if (in0 == nullptr || weight == nullptr || bias == nullptr || out_bf16 == nullptr || (ksize % 2) != 1) return DDM_E_BAD_ARGUMENT;
-    if (ddm::stem_smem_bytes(c0 + c1 + c2, Cout, ksize) > 200 * 1024 || B > 65535) return DDM_E_UNSUPPORTED;
     if ((Cout % 8) != 0 || !aligned16(out_bf16)) return DDM_E_ALIGNMENT;
+    if (B > 65535) return DDM_E_UNSUPPORTED;
+    if (ddm::stem_tc_supported(c0 + c1 + c2, Cout, ksize)) {      // tensor-core path (mma.sync implicit GEMM)
+        ddm::launch_stem_tc(in0, c0, in1, c1, in2, c2, weight, bias, out_bf16, B, H, W, Cout, ksize, as_stream(stream));
+        return finish(1);
+    }
+    if (ddm::stem_smem_bytes(c0 + c1 + c2, Cout, ksize) > 200 * 1024) return DDM_E_UNSUPPORTED;
     ddm::launch_stem(in0, c0, in1, c1, in2, c2, weight, bias, out_bf16, B, H, W, Cout, ksize, as_stream(stream));
     return finish(1);
 }

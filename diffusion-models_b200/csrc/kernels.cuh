@@ -24,6 +24,12 @@ void launch_finalize(const float* x, float* y, int unnorm, long long numel, cuda
 void launch_select_row(const float* table, const int* step_counter, float* dst, int row_len, cudaStream_t s);
 void launch_randn(float* x, unsigned long long seed, unsigned long long sid, long long numel, cudaStream_t s);
 
+// stem_tc.cu
+bool stem_tc_supported(int Cin, int Cout, int ks);
+int stem_tc_prepare_attributes();
+void launch_stem_tc(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* w, const float* b,
+                    void* out, int B, int H, int W, int Cout, int ks, cudaStream_t s);
+
 // linattn_tc.cu
 void launch_linattn32_tc(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int n_mem, cudaStream_t s);
 
