@@ -7,6 +7,7 @@
 #include <cudaTypedefs.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "conv_tc.cuh"
@@ -17,6 +18,7 @@ namespace {
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 0;
 bool g_ready = false;
+int g_conv_debug = 0;
 std::atomic<long long> g_launches{0};
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -86,6 +88,7 @@ int ddm_init(int device) {
     if (r != 0) return r;
     r = ddm::stem_tc_prepare_attributes();
     if (r != 0) return r;
+    if (const char* dbg = std::getenv("DDM_CONV_DEBUG")) g_conv_debug = std::atoi(dbg);   // bottleneck bisection, see conv_tc.cuh
     g_ready = true;
     return 0;
 }
@@ -194,6 +197,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.out = a->out; p.out_f32_nchw = a->out_f32_nchw; p.ld_out = a->ld_out;
     p.OH = a->OH; p.OW = a->OW; p.oy = a->oy; p.ox = a->ox; p.sy = a->sy; p.sx = a->sx;
     p.rnorm_out = a->rnorm_out;
+    p.debug = g_conv_debug;
 
     CUtensorMap tmA0, tmA1, tmW, tmOut;
     const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};

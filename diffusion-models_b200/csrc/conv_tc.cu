@@ -18,7 +18,7 @@ struct alignas(8) ConvBarriers {
 
 constexpr int kEpiThreads = 32 * kEpilogueWarps;   // 512
 constexpr int kParts = kEpilogueWarps / 4;         // column parts per accumulator row
-constexpr int kBarPre = 1, kBarPost = 2;           // named barriers of the epilogue warps
+constexpr int kBarPre = 1, kBarPost = 2, kBarRes = 3;   // named barriers of the epilogue warps
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2 : one MUFU op per element
 __device__ __forceinline__ float silu_f(float v) {
@@ -80,7 +80,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 1);
-            mbar_init(&bars->acc_empty[a], kEpiThreads);
+            mbar_init(&bars->acc_empty[a], kEpilogueWarps);
         }
         mbar_init(&bars->w_full, 1);
         fence_barrier_init();
@@ -136,8 +136,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     for (int c = 0; c < chunks_per_tap; ++c) {
                         mbar_wait(&bars->empty[stage], phase ^ 1u);
                         uint8_t* a_dst = smem + stage * stage_bytes;
+                        if (p.debug & 4) {       // profiling: no A traffic
+                            mbar_arrive_expect_tx(&bars->full[stage], static_cast<uint32_t>(stage_bytes - plan.a_bytes));
+                            if (stage_bytes == plan.a_bytes) { if (++stage == p.num_stages) { stage = 0; phase ^= 1u; } continue; }
+                        } else {
                         mbar_arrive_expect_tx(&bars->full[stage], static_cast<uint32_t>(stage_bytes));
-                        if (c < p.chunks0) {
+                        }
+                        if (p.debug & 4) {
+                        } else if (c < p.chunks0) {
                             tma_load_5d(a_dst, &tmA0, &bars->full[stage], c * kChunkK, cx, cp, cy, b0);
                         } else {
                             tma_load_5d(a_dst, &tmA1, &bars->full[stage], (c - p.chunks0) * kChunkK, cx, cp, cy, b0);
@@ -156,33 +162,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kTileM, static_cast<uint32_t>(p.block_n));
+            // Only the start-address field (bits 0-13, address >> 4) of the smem descriptors changes: build the
+            // constant part once and add precomputed 16-byte-unit offsets, so that the issue loop is a handful of
+            // integer ops per tcgen05.mma (a single thread issues every MMA of the CTA).
+            const uint64_t desc_base = umma_desc_sw128(0);
+            const uint32_t smem_lo = smem_u32(smem) >> 4;
+            const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
+            const uint32_t dy_step = static_cast<uint32_t>(p.bw * (kChunkK * 2)) >> 4;
+            const uint32_t bchunk_step = static_cast<uint32_t>(plan.b_chunk_bytes) >> 4;
+            const uint32_t b_in_stage = static_cast<uint32_t>(plan.a_bytes) >> 4;
+            const uint32_t wres_lo = smem_u32(wres) >> 4;
+            const int n_dy = p.n_dy;
+            const bool resident = p.b_resident != 0;
+            const bool do_mma = (p.debug & 2) == 0;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            if (p.b_resident) mbar_wait(&bars->w_full, 0);
+            if (resident) mbar_wait(&bars->w_full, 0);
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
                 uint32_t accumulate = 0;
                 for (int s = 0; s < p.n_slabs; ++s) {
+                    const uint32_t t0 = static_cast<uint32_t>(p.slab_tap[s][0] * chunks_per_tap) * bchunk_step;
+                    const uint32_t t1 = static_cast<uint32_t>(p.slab_tap[s][1] * chunks_per_tap) * bchunk_step;
+                    const uint32_t t2 = static_cast<uint32_t>(p.slab_tap[s][2] * chunks_per_tap) * bchunk_step;
                     for (int c = 0; c < chunks_per_tap; ++c) {
                         mbar_wait(&bars->full[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-                        for (int j = 0; j < p.n_dy; ++j) {
-                            // dy shift = j image rows = j * bw pixels = j * bw * 128 bytes (1024B-aligned) into the slab
-                            const uint64_t a_desc = umma_desc_sw128(a_addr + j * p.bw * (kChunkK * 2));
-                            const uint32_t b_addr = p.b_resident
-                                ? smem_u32(wres) + (p.slab_tap[s][j] * chunks_per_tap + c) * plan.b_chunk_bytes
-                                : a_addr + plan.a_bytes + j * plan.b_chunk_bytes;
-                            const uint64_t b_desc = umma_desc_sw128(b_addr);
+                        const uint32_t a_lo = smem_lo + static_cast<uint32_t>(stage) * stage_step;
+                        const uint32_t bres = wres_lo + static_cast<uint32_t>(c) * bchunk_step;
+                        if (do_mma) {
 #pragma unroll
-                            for (int k = 0; k < kChunkK / 16; ++k) {
-                                // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-                                umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
-                                accumulate = 1u;
+                            for (int j = 0; j < 3; ++j) {
+                                if (j < n_dy) {
+                                    // dy shift = j image rows = j * bw * 128 bytes (1024B-aligned) into the slab
+                                    const uint64_t a_desc = desc_base | static_cast<uint64_t>(a_lo + j * dy_step);
+                                    const uint32_t b_lo = resident ? bres + (j == 0 ? t0 : (j == 1 ? t1 : t2))
+                                                                   : a_lo + b_in_stage + j * bchunk_step;
+                                    const uint64_t b_desc = desc_base | static_cast<uint64_t>(b_lo);
+#pragma unroll
+                                    for (int k = 0; k < kChunkK / 16; ++k) {
+                                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 units
+                                        umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
+                                        accumulate = 1u;
+                                    }
+                                }
                             }
                         }
                         umma_commit(&bars->empty[stage]);
@@ -238,10 +265,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int c_lo = min(nchunks, part * per);
             const int c_hi = min(nchunks, c_lo + per);
 
-            // residual rows are fetched before waiting for the accumulator so that their latency hides behind the MMA
+            // Residual tile.  With TMA stores the tile is first copied, coalesced and asynchronously (cp.async), into
+            // the staging buffer in the staging layout, before waiting for the accumulator: pass 2 then reads its
+            // residual from shared memory and overwrites it with the result.  Otherwise each thread prefetches the
+            // first two 16-column chunks of its own row into registers.
+            const bool res_smem = (p.residual != nullptr) && p.tma_store;
             uint4 rpre[2][2];
-            const bool res_vec = (p.residual != nullptr) && valid && ((p.N & 15) == 0);
+            const bool res_vec = (p.residual != nullptr) && !res_smem && valid && ((p.N & 15) == 0);
             const __nv_bfloat16* rrow = p.residual != nullptr ? p.residual + out_pix * p.ld_res + n0 : nullptr;
+            if (res_smem) {
+                if (store_leader) bulk_wait_group_read<0>();       // previous tile's TMA store has drained the buffer
+                named_bar_sync(kBarRes, kEpiThreads);
+                const int upr = ncols >> 3;                         // 16-byte units per row
+                const int et = threadIdx.x - 64;                    // 0..511
+                for (int u = et; u < kTileM * upr; u += kEpiThreads) {
+                    const int row = u / upr, cu = u - row * upr;
+                    const int rx = x0 + (row & (p.bw - 1));
+                    const int ry = y0 + ((row >> p.bw_shift) & (p.bh - 1));
+                    const int rb = b0 + (row >> (p.bw_shift + p.bh_shift));
+                    uint8_t* dst = staging + (cu >> 3) * (kTileM * 128) + row * 128 + (((cu & 7) ^ (row & 7)) << 4);
+                    if (rx < p.W && ry < p.H && rb < p.B) {
+                        const long long pix = (static_cast<long long>(rb) * p.OH + (ry * p.sy + p.oy)) * p.OW + (rx * p.sx + p.ox);
+                        cp_async_16(dst, p.residual + pix * p.ld_res + n0 + cu * 8);
+                    } else {
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                    }
+                }
+                cp_async_commit();
+            }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 if (res_vec && c_lo + i < c_hi) {
@@ -252,6 +303,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
+            if (p.debug & 1) {                // profiling: epilogue does nothing but release the accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                continue;
+            }
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.acc_stride);
 
             if (p.norm_g != nullptr) {
@@ -279,6 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             // the previous tile's TMA stores must have finished reading the staging buffer before it is rewritten
             if (p.tma_store && store_leader) bulk_wait_group_read<0>();
+            if (res_smem) cp_async_wait_all();     // own residual copies landed; the barrier publishes everyone's
             named_bar_sync(kBarPre, kEpiThreads);
             float rinv = 1.0f;
             if (p.norm_g != nullptr)
@@ -293,7 +352,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (c == c_hi - 1) {
                     // last TMEM read of this accumulator stage: hand it back to the MMA warp before the stores
                     tc_fence_before();
-                    mbar_arrive(&bars->acc_empty[acc]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);     // one arrival per epilogue warp
                 }
                 float f[16];
                 const int nb = n0 + c * 16;
@@ -337,7 +397,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     continue;
                 }
-                if (p.residual != nullptr && valid) {
+                if (res_smem) {
+                    const int cl = c * 16;
+                    const uint8_t* rowp = staging + (cl >> 6) * (kTileM * 128) + r * 128;
+                    const int u = (cl & 63) >> 3;
+                    const uint4 r0 = *reinterpret_cast<const uint4*>(rowp + (((u) ^ (r & 7)) << 4));
+                    const uint4 r1 = *reinterpret_cast<const uint4*>(rowp + (((u + 1) ^ (r & 7)) << 4));
+                    f[0] += bf16_lo(r0.x); f[1] += bf16_hi(r0.x); f[2] += bf16_lo(r0.y); f[3] += bf16_hi(r0.y);
+                    f[4] += bf16_lo(r0.z); f[5] += bf16_hi(r0.z); f[6] += bf16_lo(r0.w); f[7] += bf16_hi(r0.w);
+                    f[8] += bf16_lo(r1.x); f[9] += bf16_hi(r1.x); f[10] += bf16_lo(r1.y); f[11] += bf16_hi(r1.y);
+                    f[12] += bf16_lo(r1.z); f[13] += bf16_hi(r1.z); f[14] += bf16_lo(r1.w); f[15] += bf16_hi(r1.w);
+                } else if (p.residual != nullptr && valid) {
                     if (res_vec) {
                         uint4 r0, r1;
                         const int i = c - c_lo;
@@ -390,7 +460,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             if (c_lo >= c_hi) {               // a warp with no columns still owes its arrival
                 tc_fence_before();
-                mbar_arrive(&bars->acc_empty[acc]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
             }
             if (p.rnorm_out != nullptr) red_b[part * kTileM + r] = out_sumsq;
             if (p.tma_store) fence_proxy_async();

@@ -92,6 +92,13 @@ __device__ __forceinline__ void bulk_wait_group() {
     asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(kPending) : "memory");
 }
 
+// Ampere-style 16-byte async copy global -> shared (LDGSTS), L2-only caching
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // named barrier among a subset of the CTA's warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");

@@ -50,6 +50,7 @@ class UnetEngine:
         self.time_ops: List[Tuple[str, Callable[[int], int]]] = []
         self.text_ops: List[Tuple[str, Callable[[int], int]]] = []
         self.taps: Dict[str, torch.Tensor] = {}  # named activations for per-layer parity tests
+        self.op_meta: Dict[str, dict] = {}       # GEMM shape / byte counts per conv launch (profiling aid)
         self.loops: Dict[tuple, dict] = {}       # cached sampling loops (tables + captured step graph), see diffusion.py
         self._w = {k: v.detach() for k, v in weights.items()}
         self._build()
@@ -105,6 +106,9 @@ class UnetEngine:
         a.sy, a.sx, a.oy, a.ox = out_map
         a.rnorm_out = _ptr(rnorm_out)
         self._keep.append(a)
+        self.op_meta[tag] = dict(M=a.B * a.H * a.W, N=a.N, K=a.K_pad, taps=a.ntaps, srcs=len(srcs),
+                                 out_bytes=a.B * a.H * a.W * a.N * (4 if out_f32_nchw else 2),
+                                 in_bytes=sum(int(x.numel()) * 2 for x in srcs) + (int(residual.numel()) * 2 if residual is not None else 0))
         fn = self.lib.ddm_conv2d
         ref = C.byref(a)
         (into if into is not None else self.ops).append((tag, lambda s, fn=fn, ref=ref: fn(ref, s)))

@@ -25,5 +25,5 @@ torch.cuda.synchronize()
 tags = [t for t, _ in eng.ops]
 out = os.path.join(ROOT, "gpurun_out", "op_tags.json")
 os.makedirs(os.path.dirname(out), exist_ok=True)
-json.dump({"B": B, "img": S, "time_ops": [t for t, _ in eng.time_ops], "body_ops": tags}, open(out, "w"))
+json.dump({"B": B, "img": S, "time_ops": [t for t, _ in eng.time_ops], "body_ops": tags, "meta": eng.op_meta}, open(out, "w"))
 print(len(eng.time_ops), "time launches +", len(tags), "body launches per forward")

@@ -29,6 +29,13 @@ for tag, k, ns in per:
     kinds[k] += ns
 for k, ns in sorted(kinds.items(), key=lambda x: -x[1]):
     print(f"  {k:34s} {ns/1e6:8.3f} ms  {100*ns/total:5.1f}%")
-print("top ops:")
-for tag, k, ns in sorted(per, key=lambda x: -x[2])[:40]:
-    print(f"  {tag:34s} {k:28s} {ns/1e3:9.1f} us {100*ns/total:5.1f}%")
+meta = tags.get("meta", {})
+print("top ops:   (TF = 2*M*N*K_pad / time; GB/s = (in+out bytes) / time)")
+for tag, k, ns in sorted(per, key=lambda x: -x[2])[:60]:
+    extra = ""
+    if tag in meta:
+        m = meta[tag]
+        tf = 2.0 * m["M"] * m["N"] * m["K"] / ns / 1e3
+        gbs = (m["in_bytes"] + m["out_bytes"]) / ns
+        extra = f" M={m['M']:8d} N={m['N']:4d} K={m['K']:5d} {tf:7.1f} TF {gbs:7.0f} GB/s"
+    print(f"  {tag:30s} {k:22s} {ns/1e3:8.1f} us {100*ns/total:5.1f}%{extra}")
