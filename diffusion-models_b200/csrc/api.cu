@@ -168,8 +168,6 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.chunks1 = a->src1 != nullptr ? (a->C1 + 63) / 64 : 0;
     if (a->ntaps * (p.chunks0 + p.chunks1) * 64 != a->K_pad) return DDM_E_BAD_ARGUMENT;
     p.k_chunks = a->ntaps * (p.chunks0 + p.chunks1);
-    p.tmem_cols = pow2_ceil(2 * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
-    p.acc_stride = p.tmem_cols / 2;
     p.n_pad = a->N_pad;
     if (p.n_pad > ddm::kMaxNPad) return DDM_E_UNSUPPORTED;
     // bf16 tiles whose channel count is a multiple of 64 leave through smem staging + TMA stores
@@ -191,6 +189,13 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
         }
         if (!done) return DDM_E_UNSUPPORTED;
     }
+    // two MMA issuer threads: K split (own accumulator each, summed in the epilogue) for narrow tiles with >= 2
+    // pipeline stages per tile, N split for wide tiles, otherwise a single issuer
+    if (p.block_n <= 128 && p.n_slabs * (p.chunks0 + p.chunks1) >= 2) p.issue_mode = 1;
+    else if (p.block_n > 128 && (p.block_n % 32) == 0) p.issue_mode = 2;
+    else p.issue_mode = 0;
+    p.tmem_cols = pow2_ceil((p.issue_mode == 1 ? 4 : 2) * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
+    p.acc_stride = p.tmem_cols / 2;
     p.bias = a->bias; p.row_scale = a->row_scale; p.norm_g = a->norm_g; p.scale_shift = a->scale_shift;
     p.ss_stride = a->ss_stride; p.act = a->act;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ld_res = a->ld_res;

@@ -76,10 +76,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], 1);
+            mbar_init(&bars->empty[s], p.issue_mode == 2 ? 2 : 1);   // N split: both issuers release a stage
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&bars->acc_full[a], 1);
+            mbar_init(&bars->acc_full[a], 2);            // one arrival per MMA issuer thread
             mbar_init(&bars->acc_empty[a], kEpilogueWarps);
         }
         mbar_init(&bars->w_full, 1);
@@ -158,20 +158,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------------------------ MMA issuers (two threads)
+        // tcgen05.mma issue blocks at the tensor pipe's rate (its queue is shallow) and one stage hand-over
+        // (mbarrier wait + commit) costs ~300 cycles of the issuing thread, so a single issuer leaves the pipe idle
+        // for that long after every stage (scripts/micro/handshake.cu).  Two issuer threads share the work so that
+        // one does its hand-over while the other is blocked feeding the pipe -- split so that the result stays
+        // bit-reproducible (every accumulator column range is only ever touched by one thread, in program order):
+        //   issue_mode 1 (K split, block_n <= 128): issuers take alternate stages and accumulate into their own
+        //                TMEM accumulator; the epilogue adds the two.
+        //   issue_mode 2 (N split, block_n > 128) : both issuers process every stage, each for one half of the
+        //                output columns (two N/2-wide MMAs per k-step).
+        //   issue_mode 0: issuer 0 does everything (single-stage tiles, odd shapes).
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kTileM, static_cast<uint32_t>(p.block_n));
+            const int me = warp - 1;
+            const int mode = p.issue_mode;
+            const int n_mma = mode == 2 ? p.block_n / 2 : p.block_n;
+            const uint32_t idesc = umma_idesc_bf16(kTileM, static_cast<uint32_t>(n_mma));
             // Only the start-address field (bits 0-13, address >> 4) of the smem descriptors changes: build the
-            // constant part once and add precomputed 16-byte-unit offsets, so that the issue loop is a handful of
-            // integer ops per tcgen05.mma (a single thread issues every MMA of the CTA).
+            // constant part once and add precomputed 16-byte-unit offsets.
             const uint64_t desc_base = umma_desc_sw128(0);
             const uint32_t smem_lo = smem_u32(smem) >> 4;
             const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
             const uint32_t dy_step = static_cast<uint32_t>(p.bw * (kChunkK * 2)) >> 4;
             const uint32_t bchunk_step = static_cast<uint32_t>(plan.b_chunk_bytes) >> 4;
             const uint32_t b_in_stage = static_cast<uint32_t>(plan.a_bytes) >> 4;
-            const uint32_t wres_lo = smem_u32(wres) >> 4;
+            const uint32_t b_half = mode == 2 ? static_cast<uint32_t>(me * n_mma * (kChunkK * 2)) >> 4 : 0u;   // B rows of my half
+            const uint32_t wres_lo = (smem_u32(wres) >> 4) + b_half;
+            const uint32_t d_off = mode == 1 ? static_cast<uint32_t>(me * p.block_n) : (mode == 2 ? static_cast<uint32_t>(me * n_mma) : 0u);
             const int n_dy = p.n_dy;
             const bool resident = p.b_resident != 0;
             const bool do_mma = (p.debug & 2) == 0;
@@ -179,52 +193,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            int g = 0;                      // global stage counter (same sequence in both issuers)
             if (resident) mbar_wait(&bars->w_full, 0);
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
-                uint32_t accumulate = 0;
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + d_off;
+                uint32_t accumulate = 0;        // my first MMA of the tile overwrites my accumulator
                 for (int s = 0; s < p.n_slabs; ++s) {
                     const uint32_t t0 = static_cast<uint32_t>(p.slab_tap[s][0] * chunks_per_tap) * bchunk_step;
                     const uint32_t t1 = static_cast<uint32_t>(p.slab_tap[s][1] * chunks_per_tap) * bchunk_step;
                     const uint32_t t2 = static_cast<uint32_t>(p.slab_tap[s][2] * chunks_per_tap) * bchunk_step;
                     for (int c = 0; c < chunks_per_tap; ++c) {
-                        mbar_wait(&bars->full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_lo = smem_lo + static_cast<uint32_t>(stage) * stage_step;
-                        const uint32_t bres = wres_lo + static_cast<uint32_t>(c) * bchunk_step;
-                        if (do_mma) {
+                        const bool mine = mode == 0 ? (me == 0) : (mode == 1 ? ((g & 1) == me) : true);
+                        if (mine) {
+                            mbar_wait(&bars->full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t a_lo = smem_lo + static_cast<uint32_t>(stage) * stage_step;
+                            const uint32_t bres = wres_lo + static_cast<uint32_t>(c) * bchunk_step;
+                            if (do_mma) {
 #pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                if (j < n_dy) {
-                                    // dy shift = j image rows = j * bw * 128 bytes (1024B-aligned) into the slab
-                                    const uint64_t a_desc = desc_base | static_cast<uint64_t>(a_lo + j * dy_step);
-                                    const uint32_t b_lo = resident ? bres + (j == 0 ? t0 : (j == 1 ? t1 : t2))
-                                                                   : a_lo + b_in_stage + j * bchunk_step;
-                                    const uint64_t b_desc = desc_base | static_cast<uint64_t>(b_lo);
+                                for (int j = 0; j < 3; ++j) {
+                                    if (j < n_dy) {
+                                        // dy shift = j image rows = j * bw * 128 bytes (1024B-aligned) into the slab
+                                        const uint64_t a_desc = desc_base | static_cast<uint64_t>(a_lo + j * dy_step);
+                                        const uint32_t b_lo = resident ? bres + (j == 0 ? t0 : (j == 1 ? t1 : t2))
+                                                                       : a_lo + b_in_stage + j * bchunk_step + b_half;
+                                        const uint64_t b_desc = desc_base | static_cast<uint64_t>(b_lo);
 #pragma unroll
-                                    for (int k = 0; k < kChunkK / 16; ++k) {
-                                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 units
-                                        umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
-                                        accumulate = 1u;
+                                        for (int k = 0; k < kChunkK / 16; ++k) {
+                                            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 units
+                                            umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
+                                            accumulate = 1u;
+                                        }
                                     }
                                 }
                             }
+                            umma_commit(&bars->empty[stage]);
                         }
-                        umma_commit(&bars->empty[stage]);
+                        ++g;
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
-                umma_commit(&bars->acc_full[acc]);
+                // acc_full expects one arrival per issuer: after this thread's MMAs retire, or at once if it had none
+                if (accumulate != 0u || !do_mma) umma_commit(&bars->acc_full[acc]); else mbar_arrive(&bars->acc_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..17)
+        // ------------------------------------------------------------------ epilogue (warps 3..18)
         // thread = (accumulator row r, column part): 4 parts x 128 rows.  Two passes over TMEM when RMSNorm is on
         // (sum of squares, then normalise); partial sums of the 4 parts meet in shared memory.
-        const int ew = warp - 2;
+        const int ew = warp - 3;
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int part = ew >> 2;               // column part handled by this warp
         const int r = q * 32 + lane;            // accumulator row == tile pixel
@@ -232,6 +252,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int by = (r >> p.bw_shift) & (p.bh - 1);
         const int bi = r >> (p.bw_shift + p.bh_shift);
         const bool store_leader = (ew == 0) && (lane == 0);
+        const bool ksplit = p.issue_mode == 1;     // two accumulators per tile (one per MMA issuer), summed here
+        const bool need_pix = (p.row_scale != nullptr) || (p.rnorm_out != nullptr) || !p.tma_store || ss_batched;
         const int tiles_xy = p.tiles_x * p.tiles_y;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -250,14 +272,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 tx = rem - ty * p.tiles_x;
             }
             const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
-            const int x = x0 + bx, y = y0 + by, b = b0 + bi;
             const int n0 = n_tile * p.block_n;
-            const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
-            const int oyy = y * p.sy + p.oy, oxx = x * p.sx + p.ox;
-            const long long out_pix = (static_cast<long long>(b) * p.OH + oyy) * p.OW + oxx;
-            const float rs = (p.row_scale != nullptr && valid)
-                                 ? __ldg(p.row_scale + (static_cast<long long>(b) * p.H + y) * p.W + x) : 1.0f;
-            const float* ssb = ss_batched ? p.scale_shift + static_cast<long long>(valid ? b : 0) * p.ss_stride : nullptr;
+            // Per-pixel addressing is only needed off the fast path (TMA store clips out-of-range rows by itself):
+            // pre-norm row scales, the row-norm side output, direct stores, per-sample scale/shift, direct residuals.
+            int b = 0, oyy = 0, oxx = 0;
+            bool valid = true;
+            long long out_pix = 0;
+            float rs = 1.0f;
+            const float* ssb = nullptr;
+            if (need_pix) {
+                const int x = x0 + bx, y = y0 + by;
+                b = b0 + bi;
+                valid = (x < p.W) && (y < p.H) && (b < p.B);
+                oyy = y * p.sy + p.oy;
+                oxx = x * p.sx + p.ox;
+                out_pix = (static_cast<long long>(b) * p.OH + oyy) * p.OW + oxx;
+                if (p.row_scale != nullptr && valid) rs = __ldg(p.row_scale + (static_cast<long long>(b) * p.H + y) * p.W + x);
+                if (ss_batched) ssb = p.scale_shift + static_cast<long long>(valid ? b : 0) * p.ss_stride;
+            }
 
             const int ncols = min(p.block_n, p.N - n0);
             const int nchunks = (ncols + 15) >> 4;
@@ -277,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (store_leader) bulk_wait_group_read<0>();       // previous tile's TMA store has drained the buffer
                 named_bar_sync(kBarRes, kEpiThreads);
                 const int upr = ncols >> 3;                         // 16-byte units per row
-                const int et = threadIdx.x - 64;                    // 0..511
+                const int et = threadIdx.x - 96;                    // 0..511
                 for (int u = et; u < kTileM * upr; u += kEpiThreads) {
                     const int row = u / upr, cu = u - row * upr;
                     const int rx = x0 + (row & (p.bw - 1));
@@ -318,7 +350,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     __syncwarp();
                     uint32_t v[16];
                     tmem_ld16(t_row + c * 16, v);
-                    tmem_ld_wait();
+                    if (ksplit) {
+                        uint32_t v2[16];
+                        tmem_ld16(t_row + p.block_n + c * 16, v2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                     const float4* b4 = reinterpret_cast<const float4*>(col_bias + n0 + c * 16);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -348,7 +388,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 __syncwarp();
                 uint32_t v[16];
                 tmem_ld16(t_row + c * 16, v);
-                tmem_ld_wait();
+                if (ksplit) {
+                    uint32_t v2[16];
+                    tmem_ld16(t_row + p.block_n + c * 16, v2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                } else {
+                    tmem_ld_wait();
+                }
                 if (c == c_hi - 1) {
                     // last TMEM read of this accumulator stage: hand it back to the MMA warp before the stores
                     tc_fence_before();

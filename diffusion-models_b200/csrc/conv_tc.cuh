@@ -6,7 +6,8 @@
 //   B tile (block_n x 64, bf16)             : 2-D TMA box of the packed weight matrix [N_pad][K_pad] (K contiguous).
 //   D (128 x block_n fp32)                  : TMEM accumulator, double buffered so the epilogue of tile i overlaps
 //     the main loop of tile i+1.
-// Warp roles: warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner, warps 2..17 = epilogue:
+// Warp roles: warp 0 = TMA producer (1 lane), warps 1-2 = MMA issuers (1 lane each, alternating pipeline stages;
+// warp 1 also owns the TMEM allocation), warps 3..18 = epilogue:
 // thread = (accumulator row, column part), so the per-pixel RMSNorm over C_out is four partial sums exchanged through
 // shared memory.  Per-column epilogue vectors (bias, norm gain x (scale+1), shift) are staged in shared memory once
 // per CTA; the bf16 output tile is staged in 128B-swizzled shared memory and written with TMA stores.
@@ -26,7 +27,7 @@ constexpr int kChunkK = 64;                       // bf16 elements per k-chunk =
 constexpr int kATileBytes = kTileM * kChunkK * 2; // 16 KiB
 constexpr int kMaxTaps = 9;
 constexpr int kEpilogueWarps = 16;
-constexpr int kConvThreads = 64 + 32 * kEpilogueWarps;   // producer warp + MMA warp + epilogue warps
+constexpr int kConvThreads = 96 + 32 * kEpilogueWarps;   // producer warp + 2 MMA issuer warps + epilogue warps
 constexpr int kMaxNPad = 512;
 
 struct ConvParams {
@@ -52,6 +53,7 @@ struct ConvParams {
     int acc_stride;              // TMEM columns between the two accumulator stages
     int tmem_cols;               // allocated TMEM columns (power of two >= 32)
     int num_stages;              // smem ring depth
+    int issue_mode;              // how the two MMA issuer threads share a tile: 0 single, 1 K split, 2 N split
     int debug;                   // profiling only (DDM_CONV_DEBUG): 1 = skip epilogue work, 2 = skip MMA issue, 4 = skip A loads
     int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)
     // epilogue
