@@ -175,6 +175,14 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if (strided_out && !(a->sy == 2 && a->sx == 2 && a->OH == 2 * a->H && a->OW == 2 * a->W)) return DDM_E_UNSUPPORTED;
     p.tma_store = (!a->out_f32_nchw && (a->N % 64) == 0 && (!strided_out || a->ld_out == a->N) && a->OH >= a->H * a->sy &&
                    a->OW >= a->W * a->sx) ? 1 : 0;
+    {   // lean epilogue kernel: staged TMA store, batch-shared scale/shift, and full tiles wherever a per-pixel side
+        // input/output (row_scale, rnorm_out) is addressed by tile offset
+        const bool full_tiles = (a->W % p.bw == 0) && (a->H % p.bh == 0) && (a->B % p.bb == 0);
+        const bool side = (a->row_scale != nullptr) || (a->rnorm_out != nullptr);
+        const bool batched_ss = (a->scale_shift != nullptr) && (a->ss_stride != 0);
+        p.fast_epilogue = (p.tma_store && !batched_ss && (!side || (full_tiles && !strided_out)) && !(g_conv_debug & 8)) ? 1 : 0;
+        p.staging_bufs = 1;
+    }
     // shared-memory configuration: prefer A-slab reuse and resident weights, as long as >= 3 pipeline stages remain
     {
         bool done = false;
@@ -188,6 +196,12 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             }
         }
         if (!done) return DDM_E_UNSUPPORTED;
+        if (p.fast_epilogue) {          // the lean kernel runs two epilogue groups, each with its own staging buffer
+            int st = 0;
+            p.staging_bufs = 2;
+            ddm::conv_smem_plan(p, &st);
+            if (st >= 2) p.num_stages = st; else { p.staging_bufs = 1; p.fast_epilogue = 0; }
+        }
     }
     // two MMA issuer threads: K split (own accumulator each, summed in the epilogue) for narrow tiles with >= 2
     // pipeline stages per tile, N split for wide tiles, otherwise a single issuer
@@ -203,7 +217,6 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.OH = a->OH; p.OW = a->OW; p.oy = a->oy; p.ox = a->ox; p.sy = a->sy; p.sx = a->sx;
     p.rnorm_out = a->rnorm_out;
     p.debug = g_conv_debug;
-
     CUtensorMap tmA0, tmA1, tmW, tmOut;
     const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};
     const unsigned abox[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh + p.n_dy - 1), static_cast<unsigned>(p.bb)};

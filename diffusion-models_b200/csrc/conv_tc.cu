@@ -16,9 +16,8 @@ struct alignas(8) ConvBarriers {
     uint32_t pad;
 };
 
-constexpr int kEpiThreads = 32 * kEpilogueWarps;   // 512
-constexpr int kParts = kEpilogueWarps / 4;         // column parts per accumulator row
-constexpr int kBarPre = 1, kBarPost = 2, kBarRes = 3;   // named barriers of the epilogue warps
+constexpr int kMaxParts = 4;                       // column parts per accumulator row (epilogue warps / 4)
+constexpr int kBarPre = 1, kBarPost = 2, kBarRes = 3, kBarAcc = 4;   // named barriers of the epilogue warps
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2 : one MUFU op per element
 __device__ __forceinline__ float silu_f(float v) {
@@ -42,17 +41,23 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
     s.stage_bytes = s.a_bytes + (p.b_resident ? 0 : p.n_dy * s.b_chunk_bytes);
     s.wres_off = num_stages * s.stage_bytes;
     s.staging_off = s.wres_off + (p.b_resident ? p.k_chunks * s.b_chunk_bytes : 0);
-    s.colp_off = s.staging_off + (p.tma_store ? kTileM * p.block_n * 2 : 0);
+    s.colp_off = s.staging_off + (p.tma_store ? (p.staging_bufs == 2 ? 2 : 1) * kTileM * p.block_n * 2 : 0);
     s.red_off = s.colp_off + 3 * p.n_pad * 4;
-    s.bars_off = s.red_off + 2 * kParts * kTileM * 4;
+    s.bars_off = s.red_off + 2 * kMaxParts * kTileM * 4;
     s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
     return s;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+// kEpiWarps epilogue warps (multiple of 4).  FAST: lean epilogue for the common case (bf16 output through smem
+// staging + TMA store, full tiles where per-pixel side inputs are used, scale/shift shared by the batch); packed
+// f32x2 arithmetic, all per-pixel address math hoisted out of the tile loop.
+template <int kEpiWarps, bool FAST>
+__global__ void __launch_bounds__(96 + 32 * kEpiWarps, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ ConvParams p) {
+    constexpr int kEpiThreads = 32 * kEpiWarps;
+    constexpr int kParts = kEpiWarps / 4;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -64,7 +69,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     float* col_mul = col_bias + p.n_pad;
     float* col_add = col_mul + p.n_pad;
     float* red_a = reinterpret_cast<float*>(smem + plan.red_off);      // [parts][128] partial sum of squares (pre-norm)
-    float* red_b = red_a + kParts * kTileM;                            // [parts][128] partial sum of squares (stored row)
+    float* red_b = red_a + kMaxParts * kTileM;                            // [parts][128] partial sum of squares (stored row)
     ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(smem + plan.bars_off);
 
     const int warp = threadIdx.x >> 5;
@@ -80,7 +85,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 2);            // one arrival per MMA issuer thread
-            mbar_init(&bars->acc_empty[a], kEpilogueWarps);
+            mbar_init(&bars->acc_empty[a], FAST ? kEpiWarps / 2 : kEpiWarps);   // FAST: one epilogue group per stage
         }
         mbar_init(&bars->w_full, 1);
         fence_barrier_init();
@@ -102,6 +107,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             m *= __ldg(p.scale_shift + n) + 1.0f;
             a = __ldg(p.scale_shift + p.N + n);
         }
+        if (FAST && p.act == 1 && affine) { m *= 0.5f; a *= 0.5f; }   // SiLU(z) = h + h tanh(h), h = z/2: fold the 1/2
         col_bias[n] = (in && p.bias != nullptr) ? __ldg(p.bias + n) : 0.0f;
         col_mul[n] = m;
         col_add[n] = a;
@@ -240,6 +246,292 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
+    } else if constexpr (FAST) {
+        // ------------------------------------------------------------------ lean epilogue (warps 3..3+kEpiWarps-1)
+        // The critical path of a tile's epilogue is ONE warp's serial instruction stream (~5 cycles per dependent
+        // instruction with few warps per scheduler), so: many warps with little work each (16 warps -> one 16-column
+        // chunk per thread for C_out = 64), no per-pixel address math unless a side input needs it, the first chunk
+        // stays in registers between the norm pass and the store pass, packed f32x2 arithmetic.
+        // Two independent epilogue groups of kEpiWarps/2 warps: group g owns accumulator stage g, staging buffer g and
+        // its own named barriers, and handles every other tile of this CTA, so two tile epilogues are in flight.
+        constexpr int kGroupWarps = kEpiWarps / 2;
+        constexpr int kGroupThreads = 32 * kGroupWarps;
+        constexpr int kGParts = kGroupWarps / 4;
+        const int grp = (warp - 3) / kGroupWarps;
+        const int ew = (warp - 3) - grp * kGroupWarps;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int part = ew >> 2;               // column part (within the group) handled by this warp
+        const int bar0 = 1 + grp * 4;           // this group's named barriers: bar0 + {0 pre, 1 post, 2 residual, 3 accumulator}
+        const int r = q * 32 + lane;            // accumulator row == tile pixel
+        const bool leader_warp = (ew == 0);
+        const bool store_leader = leader_warp && (lane == 0);
+        const bool ksplit = p.issue_mode == 1;
+        const bool has_norm = p.norm_g != nullptr;
+        const bool has_act = p.act == 1;
+        const bool act_prescaled = has_act && affine;
+        const bool res_smem = p.residual != nullptr;
+        const bool want_rs = p.row_scale != nullptr, want_rn = p.rnorm_out != nullptr;
+        const bool need_geo = leader_warp || res_smem || want_rs || want_rn;   // who needs the tile's coordinates
+        const bool skip = (p.debug & 1) != 0;   // profiling: no epilogue math / stores
+        const int stg_bytes = kTileM * p.block_n * 2;
+        const int tiles_xy = p.tiles_x * p.tiles_y;
+        // offset of this thread's pixel inside a (full) tile of the [B,H,W] grid, for row_scale / rnorm_out
+        const int row_off = ((r >> (p.bw_shift + p.bh_shift)) * p.H + ((r >> p.bw_shift) & (p.bh - 1))) * p.W + (r & (p.bw - 1));
+        const int sw = r & 7;
+        const int et = threadIdx.x - 96 - grp * kGroupThreads;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t k2_off = static_cast<uint32_t>(p.block_n);
+
+        struct TileGeo { int x0, y0, b0; };
+        auto decode = [&](int m_tile) {
+            TileGeo t;
+            int tx, ty, tb;
+            if (p.tiles_pow2) {
+                tx = m_tile & (p.tiles_x - 1);
+                ty = (m_tile >> p.tx_shift) & (p.tiles_y - 1);
+                tb = m_tile >> (p.tx_shift + p.ty_shift);
+            } else {
+                tb = m_tile / tiles_xy;
+                const int rem = m_tile - tb * tiles_xy;
+                ty = rem / p.tiles_x;
+                tx = rem - ty * p.tiles_x;
+            }
+            t.x0 = tx * p.bw; t.y0 = ty * p.bh; t.b0 = tb * p.bb;
+            return t;
+        };
+        // residual tile -> staging buffer in the staging layout (coalesced 16-byte cp.async by all epilogue threads)
+        auto fetch_residual = [&](int tile, uint8_t* buf) {
+            const int n_tile = tile >= p.m_tiles ? 1 : 0;
+            const TileGeo t = decode(tile - n_tile * p.m_tiles);
+            const int n0 = n_tile * p.block_n;
+            const int upr = min(p.block_n, p.N - n0) >> 3;       // 16-byte units per row
+            for (int u = et; u < kTileM * upr; u += kGroupThreads) {
+                const int row = u / upr, cu = u - row * upr;
+                const int rx = t.x0 + (row & (p.bw - 1));
+                const int ry = t.y0 + ((row >> p.bw_shift) & (p.bh - 1));
+                const int rb = t.b0 + (row >> (p.bw_shift + p.bh_shift));
+                uint8_t* dst = buf + (cu >> 3) * (kTileM * 128) + row * 128 + (((cu & 7) ^ (row & 7)) << 4);
+                if (rx < p.W && ry < p.H && rb < p.B) {
+                    const long long pix = (static_cast<long long>(rb) * p.OH + (ry * p.sy + p.oy)) * p.OW + (rx * p.sx + p.ox);
+                    cp_async_16(dst, p.residual + pix * p.ld_res + n0 + cu * 8);
+                } else {
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            cp_async_commit();
+        };
+        // accumulator chunk (16 columns) of this thread's row: TMEM -> 8 register pairs, K-split halves summed
+        auto load_chunk = [&](uint32_t taddr, uint64_t (&v)[8]) {
+            tmem_ld16x2(taddr, v);
+            if (ksplit) {
+                uint64_t w2[8];
+                tmem_ld16x2(taddr + k2_off, w2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], w2[j]);
+            } else {
+                tmem_ld_wait();
+            }
+        };
+        // chunk range of this thread for each of the (at most two) N tiles
+        int clo[2], chi[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int nc = min(p.block_n, p.N - t * p.block_n);
+            const int nch = nc > 0 ? (nc + 15) >> 4 : 0;
+            const int per = (nch + kGParts - 1) / kGParts;
+            clo[t] = min(nch, part * per);
+            chi[t] = min(nch, clo[t] + per);
+        }
+        const uint64_t half2 = pk2(0.5f, 0.5f);
+        const int acc = grp;                     // tile sequence number parity == group == accumulator stage
+        uint32_t acc_phase = 0;
+        uint8_t* const buf = staging + grp * stg_bytes;
+        float* const gred_a = red_a + grp * kGParts * kTileM;
+        float* const gred_b = red_b + grp * kGParts * kTileM;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
+            const int n_tile = tile >= p.m_tiles ? 1 : 0;
+            const int n0 = n_tile * p.block_n;
+            const int c_lo = n_tile ? clo[1] : clo[0], c_hi = n_tile ? chi[1] : chi[0];
+            TileGeo tg = {0, 0, 0};
+            int tile_pix = 0;
+            uint64_t rs2 = pk2(1.0f, 1.0f);
+            if (need_geo) {
+                tg = decode(tile - n_tile * p.m_tiles);
+                if (want_rs || want_rn) {
+                    tile_pix = (tg.b0 * p.H + tg.y0) * p.W + tg.x0 + row_off;     // full tiles only (host-checked)
+                    if (want_rs) { const float rs = __ldg(p.row_scale + tile_pix); rs2 = pk2(rs, rs); }
+                }
+            }
+            if (res_smem) {     // the group's previous TMA store must have drained its staging buffer before the fetch
+                if (store_leader) bulk_wait_group_read<0>();
+                named_bar_sync(bar0 + 2, kGroupThreads);
+                fetch_residual(tile, buf);
+            }
+
+            // one thread polls the mbarrier; the other epilogue warps park in a hardware named barrier (16 polling
+            // warps slow down every other mbarrier operation of the CTA)
+            if (store_leader) mbar_wait(&bars->acc_full[acc], acc_phase);
+            named_bar_sync(bar0 + 3, kGroupThreads);
+            tc_fence_after();
+            const uint32_t t_row = t_lane + static_cast<uint32_t>(acc * p.acc_stride);
+            const bool one_chunk = (c_hi - c_lo) == 1;
+
+            // ---- pass 1: bias (+ row scale), sum of squares; the first chunk stays in registers
+            uint64_t keep[8];
+            bool released = false;
+            if (c_lo < c_hi && !skip) {
+                uint64_t s01 = 0ull, s23 = 0ull;
+                for (int c = c_lo; c < c_hi; ++c) {
+                    if (!has_norm && c > c_lo) break;             // without a norm only the kept chunk is prepared here
+                    __syncwarp();
+                    uint64_t v[8];
+                    load_chunk(t_row + c * 16, v);
+                    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(col_bias + n0 + c * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const ulonglong2 bb = b2[j];
+                        v[2 * j] = ffma2(v[2 * j], rs2, bb.x);
+                        v[2 * j + 1] = ffma2(v[2 * j + 1], rs2, bb.y);
+                        s01 = ffma2(v[2 * j], v[2 * j], s01);
+                        s23 = ffma2(v[2 * j + 1], v[2 * j + 1], s23);      // padded columns have acc == 0 and bias == 0
+                    }
+                    if (c == c_lo) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) keep[j] = v[j];
+                    }
+                }
+                if (has_norm) {
+                    float a0, a1, a2, a3;
+                    upk2(s01, a0, a1);
+                    upk2(s23, a2, a3);
+                    gred_a[part * kTileM + r] = (a0 + a1) + (a2 + a3);
+                }
+                if (one_chunk) {            // nothing more to read from TMEM: release the accumulator right away
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+                    released = true;
+                }
+            }
+            // the staging buffer about to be written must have been drained by its previous TMA store
+            if (store_leader && !res_smem) bulk_wait_group_read<0>();
+            if (res_smem) cp_async_wait_all();
+            named_bar_sync(bar0, kGroupThreads);
+            uint64_t rinv2 = pk2(1.0f, 1.0f);
+            if (has_norm && !skip) {
+                float t = gred_a[r];
+#pragma unroll
+                for (int i = 1; i < kGParts; ++i) t += gred_a[i * kTileM + r];
+                const float rinv = 1.0f / fmaxf(sqrtf(t), 1e-12f);
+                rinv2 = pk2(rinv, rinv);
+            }
+
+            // ---- pass 2: normalise, scale/shift, SiLU, residual, bf16 -> staging
+            float out_sumsq = 0.0f;
+            uint8_t* const my_row = buf + r * 128;
+            for (int c = c_lo; c < c_hi && !skip; ++c) {
+                uint64_t v[8];
+                const int nb = n0 + c * 16;
+                if (c == c_lo) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = keep[j];
+                } else {
+                    __syncwarp();
+                    load_chunk(t_row + c * 16, v);
+                    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(col_bias + nb);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const ulonglong2 bb = b2[j];
+                        v[2 * j] = ffma2(v[2 * j], rs2, bb.x);
+                        v[2 * j + 1] = ffma2(v[2 * j + 1], rs2, bb.y);
+                    }
+                }
+                if (c == c_hi - 1 && !released) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);     // one arrival per epilogue warp
+                    released = true;
+                }
+                if (affine) {
+                    const ulonglong2* m2 = reinterpret_cast<const ulonglong2*>(col_mul + nb);
+                    const ulonglong2* a2p = reinterpret_cast<const ulonglong2*>(col_add + nb);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const ulonglong2 mm = m2[j], aa = a2p[j];
+                        v[2 * j] = ffma2(fmul2(v[2 * j], rinv2), mm.x, aa.x);
+                        v[2 * j + 1] = ffma2(fmul2(v[2 * j + 1], rinv2), mm.y, aa.y);
+                    }
+                }
+                if (has_act) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint64_t h = act_prescaled ? v[j] : fmul2(v[j], half2);
+                        float h0, h1;
+                        upk2(h, h0, h1);
+                        v[j] = ffma2(h, pk2(tanh_approx(h0), tanh_approx(h1)), h);
+                    }
+                }
+                const int cl = c * 16;                       // column inside this N tile
+                uint8_t* rowp = my_row + (cl >> 6) * (kTileM * 128);
+                const int u = (cl & 63) >> 3;                // 16-byte unit inside the 128-byte row
+                uint4* s0 = reinterpret_cast<uint4*>(rowp + (((u) ^ sw) << 4));
+                uint4* s1 = reinterpret_cast<uint4*>(rowp + (((u + 1) ^ sw) << 4));
+                if (res_smem) {
+                    const uint4 r0 = *s0, r1 = *s1;
+                    v[0] = fadd2(v[0], bf2_to_f2(r0.x)); v[1] = fadd2(v[1], bf2_to_f2(r0.y));
+                    v[2] = fadd2(v[2], bf2_to_f2(r0.z)); v[3] = fadd2(v[3], bf2_to_f2(r0.w));
+                    v[4] = fadd2(v[4], bf2_to_f2(r1.x)); v[5] = fadd2(v[5], bf2_to_f2(r1.y));
+                    v[6] = fadd2(v[6], bf2_to_f2(r1.z)); v[7] = fadd2(v[7], bf2_to_f2(r1.w));
+                }
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float f0, f1;
+                    upk2(v[j], f0, f1);
+                    w[j] = pack_bf16x2(f0, f1);
+                }
+                if (want_rn) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = bf16_lo(w[j]), c2 = bf16_hi(w[j]);
+                        out_sumsq = fmaf(a, a, fmaf(c2, c2, out_sumsq));
+                    }
+                }
+                *s0 = make_uint4(w[0], w[1], w[2], w[3]);
+                *s1 = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            if (!released) {                  // a warp that read nothing still owes its arrival
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+            }
+            if (want_rn) gred_b[part * kTileM + r] = out_sumsq;
+            fence_proxy_async();
+            named_bar_sync(bar0 + 1, kGroupThreads);
+            if (store_leader) {
+                if (!skip) {
+                    const int groups = (min(p.block_n, p.N - n0) + 63) >> 6;
+                    for (int g = 0; g < groups; ++g) {
+                        const int ch = n0 + g * 64;
+                        if (p.sy == 2) {     // sub-pixel phase: output viewed as [B, H, (py), W, (px c)]
+                            tma_store_5d(&tmOut, buf + g * (kTileM * 128), p.ox * p.ld_out + ch, tg.x0, p.oy, tg.y0, tg.b0);
+                        } else {
+                            tma_store_5d(&tmOut, buf + g * (kTileM * 128), ch, tg.x0, 0, tg.y0, tg.b0);
+                        }
+                    }
+                }
+                bulk_commit_group();         // (possibly empty) group: keeps the wait_group arithmetic uniform
+            }
+            if (want_rn && part == 0 && !skip) {
+                float t = gred_b[r];
+#pragma unroll
+                for (int i = 1; i < kGParts; ++i) t += gred_b[i * kTileM + r];
+                p.rnorm_out[tile_pix] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
+            }
+            acc_phase ^= 1u;
+        }
+        if (store_leader) bulk_wait_group<0>();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 3..18)
         // thread = (accumulator row r, column part): 4 parts x 128 rows.  Two passes over TMEM when RMSNorm is on
@@ -333,7 +625,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
             }
 
-            mbar_wait(&bars->acc_full[acc], acc_phase);
+            if (lane == 0) mbar_wait(&bars->acc_full[acc], acc_phase);   // one polling lane per warp: 512 pollers saturate the smem pipe
+            __syncwarp();
             tc_fence_after();
             if (p.debug & 1) {                // profiling: epilogue does nothing but release the accumulator
                 tc_fence_before();
@@ -553,7 +846,9 @@ int conv_smem_plan(const ConvParams& p, int* num_stages) {
 }
 
 int conv_prepare_attributes() {
-    return static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return r;
 }
 
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
@@ -561,7 +856,11 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     int stages = 0;
     const int smem = conv_smem_plan(p, &stages);
-    conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(tmA0, tmA1, tmW, tmOut, p);
+    if (p.fast_epilogue) {
+        conv_tc_kernel<16, true><<<grid, 96 + 32 * 16, smem, stream>>>(tmA0, tmA1, tmW, tmOut, p);
+    } else {
+        conv_tc_kernel<16, false><<<grid, 96 + 32 * 16, smem, stream>>>(tmA0, tmA1, tmW, tmOut, p);
+    }
 }
 
 }  // namespace ddm

@@ -26,8 +26,6 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements per k-chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * kChunkK * 2; // 16 KiB
 constexpr int kMaxTaps = 9;
-constexpr int kEpilogueWarps = 16;
-constexpr int kConvThreads = 96 + 32 * kEpilogueWarps;   // producer warp + 2 MMA issuer warps + epilogue warps
 constexpr int kMaxNPad = 512;
 
 struct ConvParams {
@@ -53,6 +51,8 @@ struct ConvParams {
     int acc_stride;              // TMEM columns between the two accumulator stages
     int tmem_cols;               // allocated TMEM columns (power of two >= 32)
     int num_stages;              // smem ring depth
+    int staging_bufs;            // 1 or 2 output staging buffers (2 only with the lean epilogue)
+    int fast_epilogue;           // 1: lean epilogue kernel (see conv_tc.cu), chosen by the host when its preconditions hold
     int issue_mode;              // how the two MMA issuer threads share a tile: 0 single, 1 K split, 2 N split
     int debug;                   // profiling only (DDM_CONV_DEBUG): 1 = skip epilogue work, 2 = skip MMA issue, 4 = skip A loads
     int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)

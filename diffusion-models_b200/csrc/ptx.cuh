@@ -152,6 +152,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+// same, delivered as 8 register pairs for the packed f32x2 pipe
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, uint64_t (&r)[8]) {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm("mov.b64 %0, {%1,%2};" : "=l"(r[j]) : "r"(v[2 * j]), "r"(v[2 * j + 1]));
+}
+
+// ---------------------------------------------------------------- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2)
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// two packed bf16 -> two fp32 (exact)
+__device__ __forceinline__ uint64_t bf2_to_f2(uint32_t u) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(u << 16), "r"(u & 0xFFFF0000u));
+    return r;
+}
+
 // UMMA shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 64 bf16 (=128 B) per row,
 // 8-row groups 1024 B apart (SBO).  LBO is ignored for swizzled K-major layouts.  Bits 46-47 = version 1 (sm_100).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
