@@ -203,12 +203,9 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             if (st >= 2) p.num_stages = st; else { p.staging_bufs = 1; p.fast_epilogue = 0; }
         }
     }
-    // two MMA issuer threads: K split (own accumulator each, summed in the epilogue) for narrow tiles with >= 2
-    // pipeline stages per tile, N split for wide tiles, otherwise a single issuer
-    if (p.block_n <= 128 && p.n_slabs * (p.chunks0 + p.chunks1) >= 2) p.issue_mode = 1;
-    else if (p.block_n > 128 && (p.block_n % 32) == 0) p.issue_mode = 2;
-    else p.issue_mode = 0;
-    p.tmem_cols = pow2_ceil((p.issue_mode == 1 ? 4 : 2) * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
+    // two MMA issuer threads taking alternate pipeline stages in token order (conv_tc.cu); DDM_CONV_DEBUG & 32 = single
+    p.issue_mode = (g_conv_debug & 32) ? 0 : 1;
+    p.tmem_cols = pow2_ceil(2 * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
     p.acc_stride = p.tmem_cols / 2;
     p.bias = a->bias; p.row_scale = a->row_scale; p.norm_g = a->norm_g; p.scale_shift = a->scale_shift;
     p.ss_stride = a->ss_stride; p.act = a->act;

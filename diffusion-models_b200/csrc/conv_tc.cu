@@ -13,7 +13,7 @@ struct alignas(8) ConvBarriers {
     uint64_t acc_empty[2];
     uint64_t w_full;
     uint32_t tmem_base;
-    uint32_t pad;
+    int issued;                  // MMA issue token: number of pipeline stages whose MMAs have all been issued
 };
 
 constexpr int kMaxParts = 4;                       // column parts per accumulator row (epilogue warps / 4)
@@ -81,13 +81,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], p.issue_mode == 2 ? 2 : 1);   // N split: both issuers release a stage
+            mbar_init(&bars->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 2);            // one arrival per MMA issuer thread
             mbar_init(&bars->acc_empty[a], FAST ? kEpiWarps / 2 : kEpiWarps);   // FAST: one epilogue group per stage
         }
         mbar_init(&bars->w_full, 1);
+        bars->issued = 0;
         fence_barrier_init();
         prefetch_tmap(&tmA0);
         prefetch_tmap(&tmA1);
@@ -165,22 +166,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
         }
     } else if (warp == 1 || warp == 2) {
-        // ------------------------------------------------------------------ MMA issuers (two threads)
-        // tcgen05.mma issue blocks at the tensor pipe's rate (its queue is shallow) and one stage hand-over
-        // (mbarrier wait + commit) costs ~300 cycles of the issuing thread, so a single issuer leaves the pipe idle
-        // for that long after every stage (scripts/micro/handshake.cu).  Two issuer threads share the work so that
-        // one does its hand-over while the other is blocked feeding the pipe -- split so that the result stays
-        // bit-reproducible (every accumulator column range is only ever touched by one thread, in program order):
-        //   issue_mode 1 (K split, block_n <= 128): issuers take alternate stages and accumulate into their own
-        //                TMEM accumulator; the epilogue adds the two.
-        //   issue_mode 2 (N split, block_n > 128) : both issuers process every stage, each for one half of the
-        //                output columns (two N/2-wide MMAs per k-step).
-        //   issue_mode 0: issuer 0 does everything (single-stage tiles, odd shapes).
+        // ------------------------------------------------------------------ MMA issuers (two threads, ordered alternation)
+        // One tcgen05.mma costs its issuing thread ~50 cycles, the pipe accepts only a few MMAs ahead, and a stage
+        // hand-over (mbarrier try_wait ~175 cycles even when complete, + tcgen05.commit ~60) is pure dead time for a
+        // single issuer (scripts/micro/*.cu).  Two issuer threads therefore take alternate pipeline stages: while one
+        // is blocked feeding the pipe, the other performs its hand-over.  To keep results bit-reproducible the MMAs
+        // must still enter the pipe in stage order: an issuer only starts stage g once `issued` says that stage g-1
+        // has been completely issued (a shared-memory token, ~30 cycle poll instead of an mbarrier round trip).
         if (lane == 0) {
             const int me = warp - 1;
-            const int mode = p.issue_mode;
-            const int n_mma = mode == 2 ? p.block_n / 2 : p.block_n;
-            const uint32_t idesc = umma_idesc_bf16(kTileM, static_cast<uint32_t>(n_mma));
+            const bool dual = p.issue_mode != 0;
+            const uint32_t idesc = umma_idesc_bf16(kTileM, static_cast<uint32_t>(p.block_n));
             // Only the start-address field (bits 0-13, address >> 4) of the smem descriptors changes: build the
             // constant part once and add precomputed 16-byte-unit offsets.
             const uint64_t desc_base = umma_desc_sw128(0);
@@ -189,12 +185,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t dy_step = static_cast<uint32_t>(p.bw * (kChunkK * 2)) >> 4;
             const uint32_t bchunk_step = static_cast<uint32_t>(plan.b_chunk_bytes) >> 4;
             const uint32_t b_in_stage = static_cast<uint32_t>(plan.a_bytes) >> 4;
-            const uint32_t b_half = mode == 2 ? static_cast<uint32_t>(me * n_mma * (kChunkK * 2)) >> 4 : 0u;   // B rows of my half
-            const uint32_t wres_lo = (smem_u32(wres) >> 4) + b_half;
-            const uint32_t d_off = mode == 1 ? static_cast<uint32_t>(me * p.block_n) : (mode == 2 ? static_cast<uint32_t>(me * n_mma) : 0u);
+            const uint32_t wres_lo = smem_u32(wres) >> 4;
             const int n_dy = p.n_dy;
             const bool resident = p.b_resident != 0;
             const bool do_mma = (p.debug & 2) == 0;
+            volatile int* issued = &bars->issued;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -204,27 +199,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + d_off;
-                uint32_t accumulate = 0;        // my first MMA of the tile overwrites my accumulator
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
+                bool first = true;              // first stage of the tile: its first MMA overwrites the accumulator
+                bool mine_any = false;
                 for (int s = 0; s < p.n_slabs; ++s) {
                     const uint32_t t0 = static_cast<uint32_t>(p.slab_tap[s][0] * chunks_per_tap) * bchunk_step;
                     const uint32_t t1 = static_cast<uint32_t>(p.slab_tap[s][1] * chunks_per_tap) * bchunk_step;
                     const uint32_t t2 = static_cast<uint32_t>(p.slab_tap[s][2] * chunks_per_tap) * bchunk_step;
                     for (int c = 0; c < chunks_per_tap; ++c) {
-                        const bool mine = mode == 0 ? (me == 0) : (mode == 1 ? ((g & 1) == me) : true);
+                        const bool mine = dual ? ((g & 1) == me) : (me == 0);
                         if (mine) {
                             mbar_wait(&bars->full[stage], phase);
                             tc_fence_after();
+                            if (dual) {         // wait for the token: every MMA of stage g-1 has been issued
+                                uint32_t spins = 0;
+                                while (*issued < g) { if (++spins > (1u << 28)) __trap(); }
+                            }
                             const uint32_t a_lo = smem_lo + static_cast<uint32_t>(stage) * stage_step;
                             const uint32_t bres = wres_lo + static_cast<uint32_t>(c) * bchunk_step;
                             if (do_mma) {
+                                uint32_t accumulate = first ? 0u : 1u;
 #pragma unroll
                                 for (int j = 0; j < 3; ++j) {
                                     if (j < n_dy) {
                                         // dy shift = j image rows = j * bw * 128 bytes (1024B-aligned) into the slab
                                         const uint64_t a_desc = desc_base | static_cast<uint64_t>(a_lo + j * dy_step);
                                         const uint32_t b_lo = resident ? bres + (j == 0 ? t0 : (j == 1 ? t1 : t2))
-                                                                       : a_lo + b_in_stage + j * bchunk_step + b_half;
+                                                                       : a_lo + b_in_stage + j * bchunk_step;
                                         const uint64_t b_desc = desc_base | static_cast<uint64_t>(b_lo);
 #pragma unroll
                                         for (int k = 0; k < kChunkK / 16; ++k) {
@@ -235,14 +236,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                     }
                                 }
                             }
+                            if (dual) { __threadfence_block(); *issued = g + 1; }     // pass the token
                             umma_commit(&bars->empty[stage]);
+                            mine_any = true;
                         }
+                        first = false;
                         ++g;
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
                 // acc_full expects one arrival per issuer: after this thread's MMAs retire, or at once if it had none
-                if (accumulate != 0u || !do_mma) umma_commit(&bars->acc_full[acc]); else mbar_arrive(&bars->acc_full[acc]);
+                if (mine_any) umma_commit(&bars->acc_full[acc]); else mbar_arrive(&bars->acc_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -265,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int r = q * 32 + lane;            // accumulator row == tile pixel
         const bool leader_warp = (ew == 0);
         const bool store_leader = leader_warp && (lane == 0);
-        const bool ksplit = p.issue_mode == 1;
+        const bool ksplit = false;     // (kept for the K-split accumulator layout; ordered alternation needs one accumulator)
         const bool has_norm = p.norm_g != nullptr;
         const bool has_act = p.act == 1;
         const bool act_prescaled = has_act && affine;
@@ -544,7 +548,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int by = (r >> p.bw_shift) & (p.bh - 1);
         const int bi = r >> (p.bw_shift + p.bh_shift);
         const bool store_leader = (ew == 0) && (lane == 0);
-        const bool ksplit = p.issue_mode == 1;     // two accumulators per tile (one per MMA issuer), summed here
+        const bool ksplit = false;
         const bool need_pix = (p.row_scale != nullptr) || (p.rnorm_out != nullptr) || !p.tma_store || ss_batched;
         const int tiles_xy = p.tiles_x * p.tiles_y;
         int acc = 0;

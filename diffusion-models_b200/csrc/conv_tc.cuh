@@ -53,7 +53,7 @@ struct ConvParams {
     int num_stages;              // smem ring depth
     int staging_bufs;            // 1 or 2 output staging buffers (2 only with the lean epilogue)
     int fast_epilogue;           // 1: lean epilogue kernel (see conv_tc.cu), chosen by the host when its preconditions hold
-    int issue_mode;              // how the two MMA issuer threads share a tile: 0 single, 1 K split, 2 N split
+    int issue_mode;              // 0: one MMA issuer thread; 1: two issuers alternating pipeline stages in token order
     int debug;                   // profiling only (DDM_CONV_DEBUG): 1 = skip epilogue work, 2 = skip MMA issue, 4 = skip A loads
     int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)
     // epilogue
