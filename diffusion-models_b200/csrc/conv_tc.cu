@@ -269,7 +269,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int r = q * 32 + lane;            // accumulator row == tile pixel
         const bool leader_warp = (ew == 0);
         const bool store_leader = leader_warp && (lane == 0);
-        const bool ksplit = false;     // (kept for the K-split accumulator layout; ordered alternation needs one accumulator)
         const bool has_norm = p.norm_g != nullptr;
         const bool has_act = p.act == 1;
         const bool act_prescaled = has_act && affine;
@@ -284,7 +283,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int sw = r & 7;
         const int et = threadIdx.x - 96 - grp * kGroupThreads;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const uint32_t k2_off = static_cast<uint32_t>(p.block_n);
 
         struct TileGeo { int x0, y0, b0; };
         auto decode = [&](int m_tile) {
@@ -324,19 +322,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             cp_async_commit();
         };
-        // accumulator chunk (16 columns) of this thread's row: TMEM -> 8 register pairs, K-split halves summed
-        auto load_chunk = [&](uint32_t taddr, uint64_t (&v)[8]) {
-            tmem_ld16x2(taddr, v);
-            if (ksplit) {
-                uint64_t w2[8];
-                tmem_ld16x2(taddr + k2_off, w2);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], w2[j]);
-            } else {
-                tmem_ld_wait();
-            }
-        };
+        // shared-space addresses of the per-column vectors, the reduction scratch and this thread's staging row
+        const uint32_t sb_bias = smem_u32(col_bias), sb_mul = smem_u32(col_mul), sb_add = smem_u32(col_add);
         // chunk range of this thread for each of the (at most two) N tiles
         int clo[2], chi[2];
 #pragma unroll
@@ -381,31 +368,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t t_row = t_lane + static_cast<uint32_t>(acc * p.acc_stride);
             const bool one_chunk = (c_hi - c_lo) == 1;
 
-            // ---- pass 1: bias (+ row scale), sum of squares; the first chunk stays in registers
-            uint64_t keep[8];
+            // ---- pass 1: bias (+ row scale), sum of squares; the first chunk (v0) stays in registers
+            uint64_t v0[8];
             bool released = false;
             if (c_lo < c_hi && !skip) {
                 uint64_t s01 = 0ull, s23 = 0ull;
-                for (int c = c_lo; c < c_hi; ++c) {
-                    if (!has_norm && c > c_lo) break;             // without a norm only the kept chunk is prepared here
-                    __syncwarp();
-                    uint64_t v[8];
-                    load_chunk(t_row + c * 16, v);
-                    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(col_bias + n0 + c * 16);
+                __syncwarp();
+                tmem_ld16x2(t_row + c_lo * 16, v0);
+                tmem_ld_wait();
+                {
+                    const uint32_t ba = sb_bias + static_cast<uint32_t>(n0 + c_lo * 16) * 4u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const ulonglong2 bb = b2[j];
-                        v[2 * j] = ffma2(v[2 * j], rs2, bb.x);
-                        v[2 * j + 1] = ffma2(v[2 * j + 1], rs2, bb.y);
-                        s01 = ffma2(v[2 * j], v[2 * j], s01);
-                        s23 = ffma2(v[2 * j + 1], v[2 * j + 1], s23);      // padded columns have acc == 0 and bias == 0
-                    }
-                    if (c == c_lo) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) keep[j] = v[j];
+                        const ulonglong2 bb = lds_128(ba + j * 16);
+                        v0[2 * j] = ffma2(v0[2 * j], rs2, bb.x);
+                        v0[2 * j + 1] = ffma2(v0[2 * j + 1], rs2, bb.y);
+                        s01 = ffma2(v0[2 * j], v0[2 * j], s01);
+                        s23 = ffma2(v0[2 * j + 1], v0[2 * j + 1], s23);    // padded columns have acc == 0 and bias == 0
                     }
                 }
                 if (has_norm) {
+                    for (int c = c_lo + 1; c < c_hi; ++c) {
+                        __syncwarp();
+                        uint64_t v[8];
+                        tmem_ld16x2(t_row + c * 16, v);
+                        tmem_ld_wait();
+                        const uint32_t ba = sb_bias + static_cast<uint32_t>(n0 + c * 16) * 4u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const ulonglong2 bb = lds_128(ba + j * 16);
+                            const uint64_t f0 = ffma2(v[2 * j], rs2, bb.x);
+                            const uint64_t f1 = ffma2(v[2 * j + 1], rs2, bb.y);
+                            s01 = ffma2(f0, f0, s01);
+                            s23 = ffma2(f1, f1, s23);
+                        }
+                    }
                     float a0, a1, a2, a3;
                     upk2(s01, a0, a1);
                     upk2(s23, a2, a3);
@@ -433,20 +430,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
             // ---- pass 2: normalise, scale/shift, SiLU, residual, bf16 -> staging
             float out_sumsq = 0.0f;
-            uint8_t* const my_row = buf + r * 128;
+            const uint32_t my_row = smem_u32(buf) + static_cast<uint32_t>(r) * 128u;
             for (int c = c_lo; c < c_hi && !skip; ++c) {
                 uint64_t v[8];
                 const int nb = n0 + c * 16;
                 if (c == c_lo) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = keep[j];
+                    for (int j = 0; j < 8; ++j) v[j] = v0[j];
                 } else {
                     __syncwarp();
-                    load_chunk(t_row + c * 16, v);
-                    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(col_bias + nb);
+                    tmem_ld16x2(t_row + c * 16, v);
+                    tmem_ld_wait();
+                    const uint32_t ba = sb_bias + static_cast<uint32_t>(nb) * 4u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const ulonglong2 bb = b2[j];
+                        const ulonglong2 bb = lds_128(ba + j * 16);
                         v[2 * j] = ffma2(v[2 * j], rs2, bb.x);
                         v[2 * j + 1] = ffma2(v[2 * j + 1], rs2, bb.y);
                     }
@@ -458,11 +456,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     released = true;
                 }
                 if (affine) {
-                    const ulonglong2* m2 = reinterpret_cast<const ulonglong2*>(col_mul + nb);
-                    const ulonglong2* a2p = reinterpret_cast<const ulonglong2*>(col_add + nb);
+                    const uint32_t ma = sb_mul + static_cast<uint32_t>(nb) * 4u, aa_ = sb_add + static_cast<uint32_t>(nb) * 4u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const ulonglong2 mm = m2[j], aa = a2p[j];
+                        const ulonglong2 mm = lds_128(ma + j * 16), aa = lds_128(aa_ + j * 16);
                         v[2 * j] = ffma2(fmul2(v[2 * j], rinv2), mm.x, aa.x);
                         v[2 * j + 1] = ffma2(fmul2(v[2 * j + 1], rinv2), mm.y, aa.y);
                     }
@@ -477,12 +474,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                 }
                 const int cl = c * 16;                       // column inside this N tile
-                uint8_t* rowp = my_row + (cl >> 6) * (kTileM * 128);
+                const uint32_t rowp = my_row + static_cast<uint32_t>((cl >> 6) * (kTileM * 128));
                 const int u = (cl & 63) >> 3;                // 16-byte unit inside the 128-byte row
-                uint4* s0 = reinterpret_cast<uint4*>(rowp + (((u) ^ sw) << 4));
-                uint4* s1 = reinterpret_cast<uint4*>(rowp + (((u + 1) ^ sw) << 4));
+                const uint32_t s0 = rowp + static_cast<uint32_t>(((u) ^ sw) << 4);
+                const uint32_t s1 = rowp + static_cast<uint32_t>(((u + 1) ^ sw) << 4);
                 if (res_smem) {
-                    const uint4 r0 = *s0, r1 = *s1;
+                    const uint4 r0 = lds_128u(s0), r1 = lds_128u(s1);
                     v[0] = fadd2(v[0], bf2_to_f2(r0.x)); v[1] = fadd2(v[1], bf2_to_f2(r0.y));
                     v[2] = fadd2(v[2], bf2_to_f2(r0.z)); v[3] = fadd2(v[3], bf2_to_f2(r0.w));
                     v[4] = fadd2(v[4], bf2_to_f2(r1.x)); v[5] = fadd2(v[5], bf2_to_f2(r1.y));
@@ -502,8 +499,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         out_sumsq = fmaf(a, a, fmaf(c2, c2, out_sumsq));
                     }
                 }
-                *s0 = make_uint4(w[0], w[1], w[2], w[3]);
-                *s1 = make_uint4(w[4], w[5], w[6], w[7]);
+                sts_128u(s0, w[0], w[1], w[2], w[3]);
+                sts_128u(s1, w[4], w[5], w[6], w[7]);
             }
             if (!released) {                  // a warp that read nothing still owes its arrival
                 tc_fence_before();
