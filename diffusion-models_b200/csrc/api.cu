@@ -279,6 +279,15 @@ int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const floa
     return finish(1);
 }
 
+int ddm_head_conv1x1(const void* x_bf16, const float* weight, const float* bias, float* out_f32_nchw, int B, int HW, int C,
+                     int N, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if ((C % 8) != 0 || !aligned16(x_bf16) || (C % 4) != 0) return DDM_E_ALIGNMENT;
+    if (N * C * 4 > 48 * 1024) return DDM_E_UNSUPPORTED;
+    const int r = ddm::launch_head_conv(x_bf16, weight, bias, out_f32_nchw, static_cast<long long>(B) * HW, C, N, HW, as_stream(stream));
+    return r != 0 ? r : finish(1);
+}
+
 int ddm_sinusoidal_embedding(const float* t, float* out, int rows, int dim, float theta, void* stream) {
     if (!g_ready) return DDM_E_NOT_INITIALISED;
     if (dim < 4 || (dim % 2) != 0 || rows < 1) return DDM_E_BAD_ARGUMENT;

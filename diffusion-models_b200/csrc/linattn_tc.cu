@@ -32,6 +32,15 @@ __device__ __forceinline__ void load_row32(const __nv_bfloat16* p, float (&f)[32
         f[8 * c + 4] = bf16_lo(u.z); f[8 * c + 5] = bf16_hi(u.z); f[8 * c + 6] = bf16_lo(u.w); f[8 * c + 7] = bf16_hi(u.w);
     }
 }
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
     const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
@@ -70,23 +79,29 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     float* scratch2 = reinterpret_cast<float*>(PV);            // [TOK][33] floats overlaying the P/V tiles
     static_assert(sizeof(__nv_bfloat16) * 2 * TOK * PITCH >= sizeof(float) * TOK * 33, "scratch overlay too small");
 
+    // Global access pattern: a token's 32 channels of one head are 64 contiguous bytes; thread t handles 16-byte
+    // part (t & 3) of token (t >> 2) + 32 i of a tile, so that a warp request touches 8 cache lines instead of 32
+    // (one thread per token made the kernel L1-wavefront-bound: l1tex 90 % busy, profiles/r01_ncu_linattn*.txt).
+    const int part = tid & 3;            // channels 8*part .. 8*part+7
+    const int trow = tid >> 2;           // token within a group of 32
+
     // ---- pass 1: per-channel max of k over the tokens (softmax over n, dd:185)
     {
-        float mx[D];
+        float mx[8];
 #pragma unroll
-        for (int c = 0; c < D; ++c) mx[c] = -INFINITY;
-        for (int tok = tid; tok < n; tok += TOK) {
-            float f[D];
-            load_row32(kp + static_cast<long long>(tok) * ld, f);
+        for (int c = 0; c < 8; ++c) mx[c] = -INFINITY;
+        for (int tok = trow; tok < n; tok += 32) {
+            float f[8];
+            load8(kp + static_cast<long long>(tok) * ld + part * 8, f);
 #pragma unroll
-            for (int c = 0; c < D; ++c) mx[c] = fmaxf(mx[c], f[c]);
+            for (int c = 0; c < 8; ++c) mx[c] = fmaxf(mx[c], f[c]);
         }
 #pragma unroll
-        for (int c = 0; c < D; ++c) red[tid * 33 + c] = mx[c];
+        for (int c = 0; c < 8; ++c) red[trow * 33 + part * 8 + c] = mx[c];
         __syncthreads();
         if (tid < D) {
             float m = -INFINITY;
-            for (int t = 0; t < TOK; ++t) m = fmaxf(m, red[t * 33 + tid]);
+            for (int t = 0; t < 32; ++t) m = fmaxf(m, red[t * 33 + tid]);
             for (int j = 0; j < n_mem; ++j) m = fmaxf(m, __ldg(mk + tid * n_mem + j));
             kmax[tid] = m;
         }
@@ -101,33 +116,50 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) cacc[i][j][e] = 0.0f;
-    float psum[D];
+    float psum[8];
+    float km[8];
 #pragma unroll
-    for (int c = 0; c < D; ++c) psum[c] = 0.0f;
+    for (int c = 0; c < 8; ++c) { psum[c] = 0.0f; km[c] = kmax[part * 8 + c]; }
 
-    for (int t0 = 0; t0 < n; t0 += TOK) {
-        const int tok = t0 + tid;
-        uint4* prow = reinterpret_cast<uint4*>(Ps + tid * PITCH);
-        uint4* vrow = reinterpret_cast<uint4*>(Vs + tid * PITCH);
-        if (tok < n) {
-            float f[D];
-            load_row32(kp + static_cast<long long>(tok) * ld, f);
-            uint32_t w[16];
+    // the next tile's k/v rows are fetched into registers while the current tile is multiplied (global latency
+    // was the limiter: 16 warps/SM, long-scoreboard stalls 8 per issue)
+    uint4 kreg[TOK / 32], vreg[TOK / 32];
+    auto fetch_kv = [&](int t0) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                w[c] = pack_bf16x2(__expf(f[2 * c] - kmax[2 * c]), __expf(f[2 * c + 1] - kmax[2 * c + 1]));
-                psum[2 * c] += bf16_lo(w[c]);          // normalise with exactly the rounded weights the MMA sees
-                psum[2 * c + 1] += bf16_hi(w[c]);
+        for (int i = 0; i < TOK / 32; ++i) {
+            const int tok = t0 + trow + 32 * i;
+            if (tok < n) {
+                kreg[i] = __ldg(reinterpret_cast<const uint4*>(kp + static_cast<long long>(tok) * ld + part * 8));
+                vreg[i] = __ldg(reinterpret_cast<const uint4*>(vp + static_cast<long long>(tok) * ld + part * 8));
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) prow[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-            const uint4* vsrc = reinterpret_cast<const uint4*>(vp + static_cast<long long>(tok) * ld);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) vrow[c] = __ldg(vsrc + c);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { prow[c] = make_uint4(0, 0, 0, 0); vrow[c] = make_uint4(0, 0, 0, 0); }
         }
+    };
+    fetch_kv(0);
+    for (int t0 = 0; t0 < n; t0 += TOK) {
+#pragma unroll
+        for (int i = 0; i < TOK / 32; ++i) {
+            const int lt = trow + 32 * i;               // token inside the tile
+            const int tok = t0 + lt;
+            uint4* pdst = reinterpret_cast<uint4*>(Ps + lt * PITCH + part * 8);
+            uint4* vdst = reinterpret_cast<uint4*>(Vs + lt * PITCH + part * 8);
+            if (tok < n) {
+                float f[8];
+                unpack8(kreg[i], f);
+                uint32_t w[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    w[c] = pack_bf16x2(__expf(f[2 * c] - km[2 * c]), __expf(f[2 * c + 1] - km[2 * c + 1]));
+                    psum[2 * c] += bf16_lo(w[c]);          // normalise with exactly the rounded weights the MMA sees
+                    psum[2 * c + 1] += bf16_hi(w[c]);
+                }
+                *pdst = make_uint4(w[0], w[1], w[2], w[3]);
+                *vdst = vreg[i];
+            } else {
+                *pdst = make_uint4(0, 0, 0, 0);
+                *vdst = make_uint4(0, 0, 0, 0);
+            }
+        }
+        if (t0 + TOK < n) fetch_kv(t0 + TOK);
         __syncthreads();
         // warp w contracts its 32 tokens: A = P^T (stored [tok][d] -> ldmatrix.trans), B = V (stored [tok][e] -> .trans)
 #pragma unroll
@@ -152,23 +184,23 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     // combine: per-warp partial contexts + per-thread partial sums + the learned memory tokens (dd:181-182)
     {
         const int g = lane >> 2, t = lane & 3;
-        float* part = red + warp * (D * D);
+        float* wpart = red + warp * (D * D);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int d0 = mt * 16 + g, e0 = nt * 8 + 2 * t;
-                part[d0 * D + e0] = cacc[mt][nt][0];
-                part[d0 * D + e0 + 1] = cacc[mt][nt][1];
-                part[(d0 + 8) * D + e0] = cacc[mt][nt][2];
-                part[(d0 + 8) * D + e0 + 1] = cacc[mt][nt][3];
+                wpart[d0 * D + e0] = cacc[mt][nt][0];
+                wpart[d0 * D + e0 + 1] = cacc[mt][nt][1];
+                wpart[(d0 + 8) * D + e0] = cacc[mt][nt][2];
+                wpart[(d0 + 8) * D + e0 + 1] = cacc[mt][nt][3];
             }
 #pragma unroll
-        for (int c = 0; c < D; ++c) scratch2[tid * 33 + c] = psum[c];
+        for (int c = 0; c < 8; ++c) scratch2[trow * 33 + part * 8 + c] = psum[c];
         __syncthreads();
         if (tid < D) {
             float s = 0.0f;
-            for (int r = 0; r < TOK; ++r) s += scratch2[r * 33 + tid];
+            for (int r = 0; r < 32; ++r) s += scratch2[r * 33 + tid];
             for (int j = 0; j < n_mem; ++j) s += __expf(__ldg(mk + tid * n_mem + j) - kmax[tid]);
             ksum[tid] = s;
         }
@@ -199,27 +231,47 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
             for (int np = 0; np < 2; ++np)
                 ldmatrix_x4_trans(cb[ks][np], Cs + (ks * 16 + j + 8 * (i & 1)) * PITCH + np * 16 + 8 * (i >> 1));
     }
-    for (int t0 = 0; t0 < n; t0 += TOK) {
-        const int tok = t0 + tid;
-        uint4* qrow = reinterpret_cast<uint4*>(Ps + tid * PITCH);
-        if (tok < n) {
-            float f[D];
-            load_row32(qp + static_cast<long long>(tok) * ld, f);
-            float m = f[0];
+    uint4 qreg[TOK / 32];
+    auto fetch_q = [&](int t0) {
 #pragma unroll
-            for (int c = 1; c < D; ++c) m = fmaxf(m, f[c]);
-            float s = 0.0f;
-#pragma unroll
-            for (int c = 0; c < D; ++c) { f[c] = __expf(f[c] - m); s += f[c]; }
-            const float inv = 1.0f / s;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                qrow[c] = make_uint4(pack_bf16x2(f[8 * c] * inv, f[8 * c + 1] * inv), pack_bf16x2(f[8 * c + 2] * inv, f[8 * c + 3] * inv),
-                                     pack_bf16x2(f[8 * c + 4] * inv, f[8 * c + 5] * inv), pack_bf16x2(f[8 * c + 6] * inv, f[8 * c + 7] * inv));
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) qrow[c] = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < TOK / 32; ++i) {
+            const int tok = t0 + trow + 32 * i;
+            if (tok < n) qreg[i] = __ldg(reinterpret_cast<const uint4*>(qp + static_cast<long long>(tok) * ld + part * 8));
         }
+    };
+    fetch_q(0);
+    for (int t0 = 0; t0 < n; t0 += TOK) {
+#pragma unroll
+        for (int i = 0; i < TOK / 32; ++i) {
+            const int lt = trow + 32 * i;
+            const int tok = t0 + lt;
+            float f[8];
+            float m = -INFINITY;
+            if (tok < n) {
+                unpack8(qreg[i], f);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) m = fmaxf(m, f[c]);
+            }
+            // softmax over the 32 channels of the token = the 4 lanes that share it (dd:184)
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            float ssum = 0.0f;
+            if (tok < n) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { f[c] = __expf(f[c] - m); ssum += f[c]; }
+            }
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+            uint4* qdst = reinterpret_cast<uint4*>(Ps + lt * PITCH + part * 8);
+            if (tok < n) {
+                const float inv = 1.0f / ssum;
+                *qdst = make_uint4(pack_bf16x2(f[0] * inv, f[1] * inv), pack_bf16x2(f[2] * inv, f[3] * inv),
+                                   pack_bf16x2(f[4] * inv, f[5] * inv), pack_bf16x2(f[6] * inv, f[7] * inv));
+            } else {
+                *qdst = make_uint4(0, 0, 0, 0);
+            }
+        }
+        if (t0 + TOK < n) fetch_q(t0 + TOK);
         __syncthreads();
         float oacc[2][4][4];
 #pragma unroll
@@ -252,11 +304,13 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
                 }
         }
         __syncthreads();
-        if (tok < n) {
-            const uint4* src = reinterpret_cast<const uint4*>(Vs + tid * PITCH);
-            uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * n + tok) * HD + h * D);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = src[c];
+        for (int i = 0; i < TOK / 32; ++i) {
+            const int lt = trow + 32 * i;
+            const int tok = t0 + lt;
+            if (tok < n)
+                *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * n + tok) * HD + h * D + part * 8) =
+                    *reinterpret_cast<const uint4*>(Vs + lt * PITCH + part * 8);
         }
         __syncthreads();
     }

@@ -217,6 +217,51 @@ rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ head conv
+// final_conv (1x1, C -> N <= 8, denoising_diffusion.py:343,390): bf16 channels-last rows -> fp32 NCHW planes.
+// HBM-bound (reads 2*C bytes per pixel): `lpr` lanes share a pixel with 16-byte loads, shuffle-reduce, coalesced plane
+// stores.  fp32 weights (no rounding of the last layer's weights).
+template <int NOUT>
+__global__ void __launch_bounds__(256)
+head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ out, long long rows, int C, int HW) {
+    extern __shared__ float head_w[];                // [NOUT][C]
+    for (int i = threadIdx.x; i < NOUT * C; i += blockDim.x) head_w[i] = __ldg(w + i);
+    __syncthreads();
+    // one thread per pixel: C/8 independent 16-byte loads in flight per thread, plane stores coalesced across the warp
+    const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    float acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = __ldg(bias + n);
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+    for (int c8 = 0; c8 < C / 8; c8 += 4) {
+        uint4 u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = (c8 + i < C / 8) ? __ldg(xr + c8 + i) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (c8 + i < C / 8) {
+                const uint32_t ww[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { f[2 * j] = bf16_lo(ww[j]); f[2 * j + 1] = bf16_hi(ww[j]); }
+                const int c = (c8 + i) * 8;
+#pragma unroll
+                for (int n = 0; n < NOUT; ++n) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(head_w + n * C + c);
+                    const float4 w1 = *reinterpret_cast<const float4*>(head_w + n * C + c + 4);
+                    acc[n] = fmaf(f[0], w0.x, fmaf(f[1], w0.y, fmaf(f[2], w0.z, fmaf(f[3], w0.w, acc[n]))));
+                    acc[n] = fmaf(f[4], w1.x, fmaf(f[5], w1.y, fmaf(f[6], w1.z, fmaf(f[7], w1.w, acc[n]))));
+                }
+            }
+        }
+    }
+    const long long b = row / HW, pix = row - b * HW;
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) out[(b * NOUT + n) * HW + pix] = acc[n];
+}
+
 // ------------------------------------------------------------------------------------------------ Philox N(0,1)
 struct Philox4 { uint32_t x, y, z, w; };
 
@@ -366,6 +411,21 @@ void launch_rmsnorm_act(const void* x, const float* g, const float* ss, long lon
     rmsnorm_act_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), g, ss, ss_stride,
                                                           rows_per_batch, act, reinterpret_cast<const __nv_bfloat16*>(res),
                                                           reinterpret_cast<__nv_bfloat16*>(out), rows, C);
+}
+int launch_head_conv(const void* x, const float* w, const float* bias, float* out, long long rows, int C, int N, int HW,
+                     cudaStream_t s) {
+    const auto* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+    const unsigned grid = blocks_for(rows, 256);
+    const int smem = N * C * 4;
+    switch (N) {
+        case 1: head_conv_kernel<1><<<grid, 256, smem, s>>>(xb, w, bias, out, rows, C, HW); return 0;
+        case 2: head_conv_kernel<2><<<grid, 256, smem, s>>>(xb, w, bias, out, rows, C, HW); return 0;
+        case 3: head_conv_kernel<3><<<grid, 256, smem, s>>>(xb, w, bias, out, rows, C, HW); return 0;
+        case 4: head_conv_kernel<4><<<grid, 256, smem, s>>>(xb, w, bias, out, rows, C, HW); return 0;
+        case 6: head_conv_kernel<6><<<grid, 256, smem, s>>>(xb, w, bias, out, rows, C, HW); return 0;
+        case 8: head_conv_kernel<8><<<grid, 256, smem, s>>>(xb, w, bias, out, rows, C, HW); return 0;
+        default: return -3;
+    }
 }
 void launch_sampler_step(int kind, float* x, const float* mo, const float* noise, long long noise_stride, float* x0_out, const float* coef, int* step_counter,
                          int advance, int objective, unsigned long long seed, long long numel, cudaStream_t s) {

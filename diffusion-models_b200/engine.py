@@ -198,8 +198,14 @@ class UnetEngine:
             x = self._attention(st.attn, x, h, w)
             x, h, w = self._resample(st, x, h, w)
         x = self._resblock(sp.final_block, [x, h0], h, w)
-        self._conv("final_conv", pack_conv(self._w["final_conv.weight"]), [x], self.out, domain=(B, h, w),
-                   bias=self._f32("final_conv.bias"), out_f32_nchw=True)
+        if sp.out_dim in (1, 2, 3, 4, 6, 8):      # HBM-bound head: dedicated kernel, fp32 weights, fp32 NCHW output
+            hw_, hb_ = self._f32("final_conv.weight"), self._f32("final_conv.bias")
+            cin = x.shape[-1]
+            self._add("final_conv", lambda s: lib.ddm_head_conv1x1(x.data_ptr(), hw_.data_ptr(), hb_.data_ptr(),
+                                                                    self.out.data_ptr(), B, h * w, cin, sp.out_dim, s))
+        else:
+            self._conv("final_conv", pack_conv(self._w["final_conv.weight"]), [x], self.out, domain=(B, h, w),
+                       bias=self._f32("final_conv.bias"), out_f32_nchw=True)
 
     def _build_time_path(self, t_in: torch.Tensor, ss_out: torch.Tensor, rows: int, into):
         """sinusoid -> Linear -> GELU -> Linear [-> text concat] -> (SiLU -> Linear) for all blocks at once."""

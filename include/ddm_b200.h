@@ -94,6 +94,11 @@ int ddm_conv2d(const ddm_conv_args* args, void* stream);
 int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* weight,
                   const float* bias, void* out_bf16, int B, int H, int W, int Cout, int ksize, void* stream);
 
+/* Head convolution (final_conv 1x1, dd:343,390): bf16 channels-last [B*HW, C] -> fp32 NCHW [B, N, HW], N in
+ * {1,2,3,4,6,8}; weight fp32 [N][C] (nn.Conv2d layout), bias fp32 [N].  HBM-bound; no weight rounding. */
+int ddm_head_conv1x1(const void* x_bf16, const float* weight, const float* bias, float* out_f32_nchw, int B, int HW, int C,
+                     int N, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * K5: time-conditioning path (dd:77-84 sinusoid, dd:280-285 time_mlp, dd:127-130 per-block SiLU -> Linear,
  * tc:146-152 text concat).  Built from two tiny kernels.

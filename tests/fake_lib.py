@@ -116,6 +116,13 @@ class FakeLib:
         self.view(out, (B, H, W, Cout), torch.bfloat16).copy_(y.to(torch.bfloat16))
         return 0
 
+    def ddm_head_conv1x1(self, x, w, b, out, B, HW, C_, N, stream):
+        self.calls += 1
+        xv = self.view(x, (B, HW, C_), torch.bfloat16).float()
+        y = xv @ self.view(w, (N, C_), torch.float32).t() + self.view(b, (N,), torch.float32)
+        self.view(out, (B, N, HW), torch.float32).copy_(y.permute(0, 2, 1))
+        return 0
+
     def ddm_sinusoidal_embedding(self, t, out, rows, dim, theta, stream):
         self.calls += 1
         self.view(out, (rows, dim), torch.float32).copy_(R.sinusoidal_ref(self.view(t, (rows,), torch.float32), dim, theta))

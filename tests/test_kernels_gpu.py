@@ -312,3 +312,16 @@ def test_philox_normal_statistics(lib):
     out = torch.zeros((n,), device="cuda")
     check(lib.ddm_finalize(x.data_ptr(), out.data_ptr(), 1, n, stream()))
     assert torch.equal(out, (x + 1) * 0.5)
+
+
+@pytest.mark.parametrize("N,C_", [(3, 64), (4, 64), (8, 32), (6, 128)])
+def test_head_conv1x1(lib, N, C_):
+    """final_conv: bf16 channels-last -> fp32 NCHW with fp32 weights (dd:343,390)."""
+    B, H, W = 3, 16, 24
+    x = dev(rnd((B, H, W, C_), 150), BF)
+    w, b = dev(rnd((N, C_), 151, C_ ** -0.5)), dev(rnd((N,), 152, 0.1))
+    out = torch.zeros((B, N, H, W), dtype=F32, device="cuda")
+    check(lib.ddm_head_conv1x1(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), B, H * W, C_, N, stream()))
+    # fp32 reference on the CPU (cuDNN would use TF32 by default)
+    ref = torch.einsum("bhwc,nc->bnhw", x.float().cpu(), w.cpu()) + b.cpu()[None, :, None, None]
+    close(out, ref, 1e-4)
