@@ -48,6 +48,7 @@ EXPORTS = {
     "ddm_error_string": (C.c_char_p, [C.c_int]),
     "ddm_launch_count": (C.c_longlong, []),
     "ddm_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "ddm_debug_conv_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "ddm_stem_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ddm_head_conv1x1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

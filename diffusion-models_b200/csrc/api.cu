@@ -214,6 +214,10 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.OH = a->OH; p.OW = a->OW; p.oy = a->oy; p.ox = a->ox; p.sy = a->sy; p.sx = a->sx;
     p.rnorm_out = a->rnorm_out;
     p.debug = g_conv_debug;
+    // streamed weights are the dominant L2->SM traffic of the wide/deep layers (every M tile re-reads the whole weight
+    // matrix): pairs of CTAs in a cluster fetch half of each chunk and multicast it (DDM_CONV_DEBUG & 64 disables)
+    p.cluster = (!p.b_resident && p.m_tiles >= 2 && (p.block_n % 16) == 0 && !(g_conv_debug & 64)) ? 2 : 1;
+    p.pairs = (p.m_tiles + 1) / 2;
     CUtensorMap tmA0, tmA1, tmW, tmOut;
     const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};
     const unsigned abox[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh + p.n_dy - 1), static_cast<unsigned>(p.bb)};
@@ -241,7 +245,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     {
         const unsigned long long dims[2] = {static_cast<unsigned long long>(a->K_pad), static_cast<unsigned long long>(a->N_pad)};
         const unsigned long long str[2] = {1ull, static_cast<unsigned long long>(a->K_pad)};
-        const unsigned wbox[2] = {64u, static_cast<unsigned>(p.block_n)};
+        const unsigned wbox[2] = {64u, static_cast<unsigned>(p.block_n / p.cluster)};
         r = encode_bf16_map(&tmW, a->weight, 2, dims, str, wbox);
         if (r != 0) return r;
     }
@@ -263,6 +267,9 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     ddm::launch_conv(tmA0, tmA1, tmW, tmOut, p, g_num_sms, as_stream(stream));
     return finish(1);
 }
+
+/* debugging aid, not part of the documented ABI surface: drains the conv kernel's device-side event trace */
+int ddm_debug_conv_trace(long long* host_pairs, int cap) { return ddm::conv_trace_read(host_pairs, cap); }
 
 int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* weight,
                   const float* bias, void* out_bf16, int B, int H, int W, int Cout, int ksize, void* stream) {

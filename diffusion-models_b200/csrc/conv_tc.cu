@@ -16,6 +16,17 @@ struct alignas(8) ConvBarriers {
     int issued;                  // MMA issue token: number of pipeline stages whose MMAs have all been issued
 };
 
+// Device-side event trace for pipeline debugging (DDM_CONV_DEBUG & 128): CTA 0 records (role, event, tile, clock).
+constexpr int kTraceRoles = 5, kTraceCap = 1024;      // per-role rings, no atomics: stores are fire-and-forget
+__device__ long long g_trace[kTraceRoles * kTraceCap * 2];
+__device__ __forceinline__ void trace_ev(bool on, int role, int ev, int idx, int& n) {
+    if (!on || n >= kTraceCap) return;
+    long long* dst = g_trace + (static_cast<size_t>(role) * kTraceCap + n) * 2;
+    dst[0] = (static_cast<long long>(role) << 48) | (static_cast<long long>(ev) << 32) | static_cast<unsigned>(idx);
+    dst[1] = clock64();
+    ++n;
+}
+
 constexpr int kMaxParts = 4;                       // column parts per accumulator row (epilogue warps / 4)
 constexpr int kBarPre = 1, kBarPost = 2, kBarRes = 3, kBarAcc = 4;   // named barriers of the epilogue warps
 
@@ -72,16 +83,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     float* red_b = red_a + kMaxParts * kTileM;                            // [parts][128] partial sum of squares (stored row)
     ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(smem + plan.bars_off);
 
-    const int warp = threadIdx.x >> 5;
+    // shuffled from lane 0 so that the compiler knows the role dispatch is warp-uniform (uniform registers, no
+    // vector->uniform election loops around every TMA / MMA instruction)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const bool ss_uniform = (p.scale_shift != nullptr) && (p.ss_stride == 0);
     const bool ss_batched = (p.scale_shift != nullptr) && (p.ss_stride != 0);
     const bool affine = (p.norm_g != nullptr) || ss_uniform;
 
+    const uint32_t cl_count = p.cluster == 2 ? 2u : 1u;     // a stage is released by the issuers of every CTA of the cluster
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], 1);
+            mbar_init(&bars->empty[s], cl_count);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 2);            // one arrival per MMA issuer thread
@@ -115,24 +129,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster == 2) cluster_sync_all();      // the peer's barriers must be initialised before anything is multicast
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     const int chunks_per_tap = p.chunks0 + p.chunks1;
+    const bool tr = (p.debug & 128) && blockIdx.x == 0;
+    int trn = 0;
+    // Tile sequence of this CTA.  Without clusters: tiles blockIdx.x, +gridDim.x, ...  With 2-CTA clusters (weights
+    // multicast): cluster c takes pair sequence c, c + n_clusters, ...; the pair's two M tiles go to the two CTAs and
+    // share the N tile.  An odd tile count leaves a phantom tile past the batch end: all its loads are zero-filled
+    // and all its stores clipped, but it keeps the cluster's barrier protocol in lockstep.
+    const int cl = p.cluster;
+    const int cl_rank = cl == 2 ? static_cast<int>(blockIdx.x & 1) : 0;
+    auto seq_tile = [&](int q, int& n_tile, int& m_tile) -> bool {
+        if (cl == 2) {
+            const int ct = static_cast<int>(blockIdx.x >> 1) + q * static_cast<int>(gridDim.x >> 1);
+            if (ct >= p.pairs * p.n_tiles) return false;
+            n_tile = ct >= p.pairs ? 1 : 0;
+            m_tile = (ct - n_tile * p.pairs) * 2 + cl_rank;
+        } else {
+            const int t = static_cast<int>(blockIdx.x) + q * static_cast<int>(gridDim.x);
+            if (t >= p.total_tiles) return false;
+            n_tile = t >= p.m_tiles ? 1 : 0;
+            m_tile = t - n_tile * p.m_tiles;
+        }
+        return true;
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            if (p.b_resident) {       // the weights of this (single) N tile are loaded once per CTA
+        {
+            if (p.b_resident && elect_one()) {       // the weights of this (single) N tile are loaded once per CTA
                 mbar_arrive_expect_tx(&bars->w_full, static_cast<uint32_t>(p.k_chunks * plan.b_chunk_bytes));
                 for (int kc = 0; kc < p.k_chunks; ++kc)
                     tma_load_2d(wres + kc * plan.b_chunk_bytes, &tmW, &bars->w_full, kc * kChunkK, 0);
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int n_tile = tile / p.m_tiles;
-                const int m_tile = tile - n_tile * p.m_tiles;
+            int n_tile, m_tile;
+            for (int q = 0; seq_tile(q, n_tile, m_tile); ++q) {
                 const int tx = m_tile % p.tiles_x;
                 const int ty = (m_tile / p.tiles_x) % p.tiles_y;
                 const int tb = m_tile / (p.tiles_x * p.tiles_y);
@@ -142,24 +178,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const int cx = x0 + p.slab_dx[s], cy = y0 + p.slab_dy0[s], cp = p.slab_p[s];
                     for (int c = 0; c < chunks_per_tap; ++c) {
                         mbar_wait(&bars->empty[stage], phase ^ 1u);
-                        uint8_t* a_dst = smem + stage * stage_bytes;
-                        if (p.debug & 4) {       // profiling: no A traffic
-                            mbar_arrive_expect_tx(&bars->full[stage], static_cast<uint32_t>(stage_bytes - plan.a_bytes));
-                            if (stage_bytes == plan.a_bytes) { if (++stage == p.num_stages) { stage = 0; phase ^= 1u; } continue; }
-                        } else {
-                        mbar_arrive_expect_tx(&bars->full[stage], static_cast<uint32_t>(stage_bytes));
+                        if (elect_one()) {
+                            trace_ev(tr, 0, 0, q, trn);
+                            uint8_t* a_dst = smem + stage * stage_bytes;
+                            const bool skip_a = (p.debug & 4) != 0;      // profiling: no A traffic
+                            const uint32_t tx_bytes = static_cast<uint32_t>(skip_a ? stage_bytes - plan.a_bytes : stage_bytes);
+                            mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
+                            if (skip_a) {
+                            } else if (c < p.chunks0) {
+                                tma_load_5d(a_dst, &tmA0, &bars->full[stage], c * kChunkK, cx, cp, cy, b0);
+                            } else {
+                                tma_load_5d(a_dst, &tmA1, &bars->full[stage], (c - p.chunks0) * kChunkK, cx, cp, cy, b0);
+                            }
+                            if (!p.b_resident) {
+                                for (int j = 0; j < p.n_dy; ++j) {
+                                    uint8_t* b_dst = a_dst + plan.a_bytes + j * plan.b_chunk_bytes;
+                                    const int kcol = (p.slab_tap[s][j] * chunks_per_tap + c) * kChunkK;
+                                    if (cl == 2) {      // each CTA fetches half of the rows and multicasts them to both
+                                        const int half_rows = p.block_n >> 1;
+                                        tma_load_2d_mc(b_dst + cl_rank * half_rows * (kChunkK * 2), &tmW, &bars->full[stage], kcol,
+                                                       n0 + cl_rank * half_rows, 0x3);
+                                    } else {
+                                        tma_load_2d(b_dst, &tmW, &bars->full[stage], kcol, n0);
+                                    }
+                                }
+                            }
+                            trace_ev(tr, 0, 1, q, trn);
                         }
-                        if (p.debug & 4) {
-                        } else if (c < p.chunks0) {
-                            tma_load_5d(a_dst, &tmA0, &bars->full[stage], c * kChunkK, cx, cp, cy, b0);
-                        } else {
-                            tma_load_5d(a_dst, &tmA1, &bars->full[stage], (c - p.chunks0) * kChunkK, cx, cp, cy, b0);
-                        }
-                        if (!p.b_resident) {
-                            for (int j = 0; j < p.n_dy; ++j)
-                                tma_load_2d(a_dst + plan.a_bytes + j * plan.b_chunk_bytes, &tmW, &bars->full[stage],
-                                            (p.slab_tap[s][j] * chunks_per_tap + c) * kChunkK, n0);
-                        }
+                        __syncwarp();
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -173,7 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // is blocked feeding the pipe, the other performs its hand-over.  To keep results bit-reproducible the MMAs
         // must still enter the pipe in stage order: an issuer only starts stage g once `issued` says that stage g-1
         // has been completely issued (a shared-memory token, ~30 cycle poll instead of an mbarrier round trip).
-        if (lane == 0) {
+        {
             const int me = warp - 1;
             const bool dual = p.issue_mode != 0;
             const uint32_t idesc = umma_idesc_bf16(kTileM, static_cast<uint32_t>(p.block_n));
@@ -195,9 +241,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             int acc = 0;
             uint32_t acc_phase = 0;
             int g = 0;                      // global stage counter (same sequence in both issuers)
-            if (resident) mbar_wait(&bars->w_full, 0);
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            if (resident) mbar_wait(&bars->w_full, 0);      // every lane waits: the loop below stays warp-uniform
+            int n_tile_unused, m_tile_unused;
+            for (int q = 0; seq_tile(q, n_tile_unused, m_tile_unused); ++q) {
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1u);
+                if (tr && lane == 0) trace_ev(tr, 1 + me, 0, q, trn);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
                 bool first = true;              // first stage of the tile: its first MMA overwrites the accumulator
@@ -210,13 +258,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         const bool mine = dual ? ((g & 1) == me) : (me == 0);
                         if (mine) {
                             mbar_wait(&bars->full[stage], phase);
+                            if (tr && lane == 0) trace_ev(tr, 1 + me, 1, g, trn);
                             tc_fence_after();
                             if (dual) {         // wait for the token: every MMA of stage g-1 has been issued
                                 uint32_t spins = 0;
                                 while (*issued < g) { if (++spins > (1u << 28)) __trap(); }
                             }
+                            if (tr && lane == 0) trace_ev(tr, 1 + me, 2, g, trn);
                             const uint32_t a_lo = smem_lo + static_cast<uint32_t>(stage) * stage_step;
                             const uint32_t bres = wres_lo + static_cast<uint32_t>(c) * bchunk_step;
+                            if (elect_one()) {
                             if (do_mma) {
                                 uint32_t accumulate = first ? 0u : 1u;
 #pragma unroll
@@ -236,8 +287,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                     }
                                 }
                             }
+                            trace_ev(tr, 1 + me, 3, g, trn);
                             if (dual) { __threadfence_block(); *issued = g + 1; }     // pass the token
-                            umma_commit(&bars->empty[stage]);
+                            if (cl == 2) umma_commit_mc(&bars->empty[stage], 0x3); else umma_commit(&bars->empty[stage]);
+                            trace_ev(tr, 1 + me, 4, g, trn);
+                            }
+                            __syncwarp();
                             mine_any = true;
                         }
                         first = false;
@@ -246,7 +301,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                 }
                 // acc_full expects one arrival per issuer: after this thread's MMAs retire, or at once if it had none
-                if (mine_any) umma_commit(&bars->acc_full[acc]); else mbar_arrive(&bars->acc_full[acc]);
+                if (elect_one()) {
+                    if (mine_any) umma_commit(&bars->acc_full[acc]); else mbar_arrive(&bars->acc_full[acc]);
+                }
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -302,9 +360,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             return t;
         };
         // residual tile -> staging buffer in the staging layout (coalesced 16-byte cp.async by all epilogue threads)
-        auto fetch_residual = [&](int tile, uint8_t* buf) {
-            const int n_tile = tile >= p.m_tiles ? 1 : 0;
-            const TileGeo t = decode(tile - n_tile * p.m_tiles);
+        auto fetch_residual = [&](int n_tile, int m_tile, uint8_t* buf) {
+            const TileGeo t = decode(m_tile);
             const int n0 = n_tile * p.block_n;
             const int upr = min(p.block_n, p.N - n0) >> 3;       // 16-byte units per row
             for (int u = et; u < kTileM * upr; u += kGroupThreads) {
@@ -340,16 +397,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint8_t* const buf = staging + grp * stg_bytes;
         float* const gred_a = red_a + grp * kGParts * kTileM;
         float* const gred_b = red_b + grp * kGParts * kTileM;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
-            const int n_tile = tile >= p.m_tiles ? 1 : 0;
+        int n_tile, m_tile;
+        for (int q = grp; seq_tile(q, n_tile, m_tile); q += 2) {
+            const bool real_tile = m_tile < p.m_tiles;          // false only for a cluster's phantom tile
             const int n0 = n_tile * p.block_n;
             const int c_lo = n_tile ? clo[1] : clo[0], c_hi = n_tile ? chi[1] : chi[0];
             TileGeo tg = {0, 0, 0};
             int tile_pix = 0;
             uint64_t rs2 = pk2(1.0f, 1.0f);
             if (need_geo) {
-                tg = decode(tile - n_tile * p.m_tiles);
-                if (want_rs || want_rn) {
+                tg = decode(m_tile);
+                if ((want_rs || want_rn) && real_tile) {
                     tile_pix = (tg.b0 * p.H + tg.y0) * p.W + tg.x0 + row_off;     // full tiles only (host-checked)
                     if (want_rs) { const float rs = __ldg(p.row_scale + tile_pix); rs2 = pk2(rs, rs); }
                 }
@@ -357,13 +415,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (res_smem) {     // the group's previous TMA store must have drained its staging buffer before the fetch
                 if (store_leader) bulk_wait_group_read<0>();
                 named_bar_sync(bar0 + 2, kGroupThreads);
-                fetch_residual(tile, buf);
+                fetch_residual(n_tile, m_tile, buf);
             }
 
             // one thread polls the mbarrier; the other epilogue warps park in a hardware named barrier (16 polling
             // warps slow down every other mbarrier operation of the CTA)
-            if (store_leader) mbar_wait(&bars->acc_full[acc], acc_phase);
+            if (store_leader) { mbar_wait(&bars->acc_full[acc], acc_phase); trace_ev(tr, 3 + grp, 0, q, trn); }
             named_bar_sync(bar0 + 3, kGroupThreads);
+            if (store_leader) trace_ev(tr, 3 + grp, 1, q, trn);
             tc_fence_after();
             const uint32_t t_row = t_lane + static_cast<uint32_t>(acc * p.acc_stride);
             const bool one_chunk = (c_hi - c_lo) == 1;
@@ -418,7 +477,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             // the staging buffer about to be written must have been drained by its previous TMA store
             if (store_leader && !res_smem) bulk_wait_group_read<0>();
             if (res_smem) cp_async_wait_all();
+            if (store_leader) trace_ev(tr, 3 + grp, 2, q, trn);
             named_bar_sync(bar0, kGroupThreads);
+            if (store_leader) trace_ev(tr, 3 + grp, 3, q, trn);
             uint64_t rinv2 = pk2(1.0f, 1.0f);
             if (has_norm && !skip) {
                 float t = gred_a[r];
@@ -509,7 +570,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             if (want_rn) gred_b[part * kTileM + r] = out_sumsq;
             fence_proxy_async();
+            if (store_leader) trace_ev(tr, 3 + grp, 4, q, trn);
             named_bar_sync(bar0 + 1, kGroupThreads);
+            if (store_leader) trace_ev(tr, 3 + grp, 5, q, trn);
             if (store_leader) {
                 if (!skip) {
                     const int groups = (min(p.block_n, p.N - n0) + 63) >> 6;
@@ -524,7 +587,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 bulk_commit_group();         // (possibly empty) group: keeps the wait_group arithmetic uniform
             }
-            if (want_rn && part == 0 && !skip) {
+            if (want_rn && part == 0 && !skip && real_tile) {
                 float t = gred_b[r];
 #pragma unroll
                 for (int i = 1; i < kGParts; ++i) t += gred_b[i * kTileM + r];
@@ -550,9 +613,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int tiles_xy = p.tiles_x * p.tiles_y;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int n_tile = tile >= p.m_tiles ? 1 : 0;          // at most two N tiles (N <= 512)
-            const int m_tile = tile - n_tile * p.m_tiles;
+        int n_tile, m_tile;
+        for (int q = 0; seq_tile(q, n_tile, m_tile); ++q) {
             int tx, ty, tb;
             if (p.tiles_pow2) {
                 tx = m_tile & (p.tiles_x - 1);
@@ -830,6 +892,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if (p.cluster == 2) cluster_sync_all();      // no CTA may exit while its peer can still multicast into it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
@@ -846,6 +909,18 @@ int conv_smem_plan(const ConvParams& p, int* num_stages) {
     return make_plan(p, stages > 0 ? stages : 1).total + 1024;
 }
 
+int conv_trace_read(long long* host, int cap) {
+    static long long tmp[kTraceRoles * kTraceCap * 2];
+    cudaMemcpyFromSymbol(tmp, g_trace, sizeof(tmp));
+    int n = 0;
+    for (int i = 0; i < kTraceRoles * kTraceCap && n < cap; ++i)
+        if (tmp[2 * i + 1] != 0) { host[2 * n] = tmp[2 * i]; host[2 * n + 1] = tmp[2 * i + 1]; ++n; }
+    void* sym = nullptr;
+    cudaGetSymbolAddress(&sym, g_trace);
+    cudaMemset(sym, 0, sizeof(tmp));
+    return n;
+}
+
 int conv_prepare_attributes() {
     int r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -854,13 +929,32 @@ int conv_prepare_attributes() {
 
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
                  const ConvParams& p, int num_sms, cudaStream_t stream) {
-    const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     int stages = 0;
     const int smem = conv_smem_plan(p, &stages);
-    if (p.fast_epilogue) {
-        conv_tc_kernel<16, true><<<grid, 96 + 32 * 16, smem, stream>>>(tmA0, tmA1, tmW, tmOut, p);
+    int grid;
+    if (p.cluster == 2) {
+        const int cluster_tiles = p.pairs * p.n_tiles;
+        const int n_clusters = cluster_tiles < num_sms / 2 ? cluster_tiles : num_sms / 2;
+        grid = 2 * n_clusters;
     } else {
-        conv_tc_kernel<16, false><<<grid, 96 + 32 * 16, smem, stream>>>(tmA0, tmA1, tmW, tmOut, p);
+        grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(96 + 32 * 16);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster == 2 ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (p.fast_epilogue) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true>, tmA0, tmA1, tmW, tmOut, p);
+    } else {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false>, tmA0, tmA1, tmW, tmOut, p);
     }
 }
 

@@ -53,6 +53,8 @@ struct ConvParams {
     int num_stages;              // smem ring depth
     int staging_bufs;            // 1 or 2 output staging buffers (2 only with the lean epilogue)
     int fast_epilogue;           // 1: lean epilogue kernel (see conv_tc.cu), chosen by the host when its preconditions hold
+    int cluster;                 // 1, or 2: CTA pairs share the (streamed) weight chunks through TMA multicast
+    int pairs;                   // ceil(m_tiles / 2) when cluster == 2
     int issue_mode;              // 0: one MMA issuer thread; 1: two issuers alternating pipeline stages in token order
     int debug;                   // profiling only (DDM_CONV_DEBUG): 1 = skip epilogue work, 2 = skip MMA issue, 4 = skip A loads
     int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)
@@ -77,5 +79,6 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
 // shared-memory plan: returns total dynamic bytes and the stage count that fits (0 stages = does not fit)
 int conv_smem_plan(const ConvParams& p, int* num_stages);
 int conv_prepare_attributes();
+int conv_trace_read(long long* host, int cap);   // debugging: device-side event trace (DDM_CONV_DEBUG & 128)
 
 }  // namespace ddm

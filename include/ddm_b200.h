@@ -86,6 +86,9 @@ typedef struct ddm_conv_args {
 } ddm_conv_args;
 
 int ddm_conv2d(const ddm_conv_args* args, void* stream);
+/* Debugging aid: with DDM_CONV_DEBUG & 128 the conv kernel records (tag, clock64) pairs from CTA 0; this drains them to
+ * host memory (synchronises the device) and returns the number of pairs.  Not used by the product path. */
+int ddm_debug_conv_trace(long long* host_pairs, int cap);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K3: stem convolution (dd:262,356; ic:46-54).  Direct k x k conv (k = 7, pad 3) over the channel-concatenation
