@@ -203,10 +203,52 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             if (st >= 2) p.num_stages = st; else { p.staging_bufs = 1; p.fast_epilogue = 0; }
         }
     }
-    // two MMA issuer threads taking alternate pipeline stages in token order (conv_tc.cu); DDM_CONV_DEBUG & 32 = single
-    p.issue_mode = (g_conv_debug & 32) ? 0 : 1;
     p.tmem_cols = pow2_ceil(2 * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
     p.acc_stride = p.tmem_cols / 2;
+    p.acc_stages = 2;
+    // dx-folded mode (conv_tc.cuh): plain 3x3, C_out padded to 64, tiles spanning whole image rows inside one warp.
+    // It cuts the L2 -> shared-memory traffic of the A slabs (the mainloop bound of these layers) at the price of a
+    // heavier epilogue, so it is used where the epilogue has slack: no residual input.  DDM_CONV_DEBUG & 512 disables it.
+    if (p.fast_epilogue && !(g_conv_debug & 512) && a->residual == nullptr && a->ntaps == 9 && a->view == 0 && p.n_tiles == 1 && p.block_n == 64 &&
+        a->N_pad == 64 && p.bw == a->W && p.bw >= 8 && p.bw <= 32 && p.bb == 1 && !strided_out) {
+        bool canonical = true;
+        unsigned seen = 0;
+        for (int t = 0; t < 9; ++t) {
+            const int dy = a->tap_dy[t], dx = a->tap_dx[t];
+            if (dy < -1 || dy > 1 || dx < -1 || dx > 1 || a->tap_p[t] != 0) { canonical = false; break; }
+            seen |= 1u << ((dy + 1) * 3 + (dx + 1));
+        }
+        if (canonical && seen == 0x1FFu) {
+            ddm::ConvParams f = p;
+            // fold = 3: one slab, all three dx groups in the accumulator (least L2 traffic, but 3x the TMEM -> register
+            // traffic and two shuffles per value in the epilogue).  fold = 2 (default): slabs dx = 0 and dx = +1, two
+            // groups, one shuffle: L2, tensor pipe and epilogue come out balanced.  DDM_CONV_DEBUG & 1024 picks 3.
+            f.fold = (g_conv_debug & 1024) ? 3 : 2;
+            f.n_slabs = f.fold == 3 ? 1 : 2; f.n_dy = 3;
+            f.slab_dx[0] = 0; f.slab_p[0] = 0; f.slab_dy0[0] = -1;
+            f.slab_dx[1] = 1; f.slab_p[1] = 0; f.slab_dy0[1] = -1;
+            for (int t = 0; t < 9; ++t) { f.fold_dyi[t] = a->tap_dy[t] + 1; f.fold_dxi[t] = a->tap_dx[t] + 1; }
+            f.a_rows = f.bw * (f.bh + 2);
+            f.b_resident = 1;
+            f.staging_bufs = 2;
+            f.tmem_cols = f.fold == 3 ? 512 : 256; f.acc_stride = f.tmem_cols / 2;
+            int st = 0;
+            ddm::conv_smem_plan(f, &st);
+            if (st >= 2) { f.num_stages = st; p = f; }
+        }
+    }
+    // Two MMA issuer threads (conv_tc.cu).  Mode 2, alternate tiles, when both threads' tiles fit in the smem ring at the
+    // same time (few stages per tile): no ordering needed between the threads.  Otherwise mode 1, alternate stages of
+    // the same tile in token order.  DDM_CONV_DEBUG & 32: single issuer; & 16384: always mode 1; & 32768: always mode 2.
+    {
+        const int stages_per_tile = p.n_slabs * (p.chunks0 + p.chunks1);
+        p.issue_mode = (g_conv_debug & 32) ? 0 : ((g_conv_debug & 16384) ? 1 : ((g_conv_debug & 32768) ? 2 : (stages_per_tile < p.num_stages ? 2 : 1)));
+    }
+    if (p.fast_epilogue && !(g_conv_debug & 2048)) {      // four accumulator stages where TMEM has room (DDM_CONV_DEBUG & 2048: two)
+        const int cols = (p.fold ? p.fold : 1) * p.block_n;
+        const int stride = pow2_ceil(cols) < 32 ? 32 : pow2_ceil(cols);
+        if (4 * stride <= 512) { p.acc_stages = 4; p.acc_stride = stride; p.tmem_cols = 4 * stride; }
+    }
     p.bias = a->bias; p.row_scale = a->row_scale; p.norm_g = a->norm_g; p.scale_shift = a->scale_shift;
     p.ss_stride = a->ss_stride; p.act = a->act;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ld_res = a->ld_res;

@@ -9,8 +9,8 @@ namespace {
 struct alignas(8) ConvBarriers {
     uint64_t full[8];
     uint64_t empty[8];
-    uint64_t acc_full[2];
-    uint64_t acc_empty[2];
+    uint64_t acc_full[4];
+    uint64_t acc_empty[4];
     uint64_t w_full;
     uint32_t tmem_base;
     int issued;                  // MMA issue token: number of pipeline stages whose MMAs have all been issued
@@ -62,7 +62,7 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
 // kEpiWarps epilogue warps (multiple of 4).  FAST: lean epilogue for the common case (bf16 output through smem
 // staging + TMA store, full tiles where per-pixel side inputs are used, scale/shift shared by the batch); packed
 // f32x2 arithmetic, all per-pixel address math hoisted out of the tile loop.
-template <int kEpiWarps, bool FAST>
+template <int kEpiWarps, bool FAST, int FOLD>
 __global__ void __launch_bounds__(96 + 32 * kEpiWarps, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
@@ -97,8 +97,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], cl_count);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&bars->acc_full[a], 2);            // one arrival per MMA issuer thread
+        for (int a = 0; a < 4; ++a) {
+            mbar_init(&bars->acc_full[a], p.issue_mode == 2 ? 1 : 2);   // per issuer thread, or (mode 2) the tile's owner only
             mbar_init(&bars->acc_empty[a], FAST ? kEpiWarps / 2 : kEpiWarps);   // FAST: one epilogue group per stage
         }
         mbar_init(&bars->w_full, 1);
@@ -135,6 +135,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     const int chunks_per_tap = p.chunks0 + p.chunks1;
     const bool tr = (p.debug & 128) && blockIdx.x == 0;
+    const bool tr_iss = (p.debug & (128 | 4096)) && blockIdx.x == 0;      // 4096: only the issuers' token/issued events
+    const bool tr_tile = (p.debug & (128 | 256)) && blockIdx.x == 0;     // 256: per-tile events only (unperturbed timing)
     int trn = 0;
     // Tile sequence of this CTA.  Without clusters: tiles blockIdx.x, +gridDim.x, ...  With 2-CTA clusters (weights
     // multicast): cluster c takes pair sequence c, c + n_clusters, ...; the pair's two M tiles go to the two CTAs and
@@ -162,8 +164,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         {
             if (p.b_resident && elect_one()) {       // the weights of this (single) N tile are loaded once per CTA
                 mbar_arrive_expect_tx(&bars->w_full, static_cast<uint32_t>(p.k_chunks * plan.b_chunk_bytes));
-                for (int kc = 0; kc < p.k_chunks; ++kc)
-                    tma_load_2d(wres + kc * plan.b_chunk_bytes, &tmW, &bars->w_full, kc * kChunkK, 0);
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    int slot = kc;
+                    if constexpr (FOLD) {       // stacked layout: block (dy, chunk) = [dx=-1 | dx=0 | dx=+1] x 64 rows
+                        const int tap = kc / chunks_per_tap, c = kc - tap * chunks_per_tap;
+                        slot = (p.fold_dyi[tap] * chunks_per_tap + c) * 3 + p.fold_dxi[tap];
+                    }
+                    tma_load_2d(wres + slot * plan.b_chunk_bytes, &tmW, &bars->w_full, kc * kChunkK, 0);
+                }
             }
             int stage = 0;
             uint32_t phase = 0;
@@ -221,8 +229,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // has been completely issued (a shared-memory token, ~30 cycle poll instead of an mbarrier round trip).
         {
             const int me = warp - 1;
-            const bool dual = p.issue_mode != 0;
-            const uint32_t idesc = umma_idesc_bf16(kTileM, static_cast<uint32_t>(p.block_n));
+            const bool dual = p.issue_mode == 1;
+            // FOLD: p.fold = 3 -> one slab, N = 3*64 (all dx groups); p.fold = 2 -> slab 0 (dx = 0) feeds the [dx=-1 | dx=0]
+            // groups with N = 128 and slab 1 (dx = +1) accumulates straight into the dx = 0 group with N = 64
+            const uint32_t idesc = umma_idesc_bf16(kTileM, static_cast<uint32_t>(FOLD ? FOLD * p.block_n : p.block_n));
+            const uint32_t idesc_n64 = umma_idesc_bf16(kTileM, static_cast<uint32_t>(p.block_n));
             // Only the start-address field (bits 0-13, address >> 4) of the smem descriptors changes: build the
             // constant part once and add precomputed 16-byte-unit offsets.
             const uint64_t desc_base = umma_desc_sw128(0);
@@ -241,11 +252,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             int acc = 0;
             uint32_t acc_phase = 0;
             int g = 0;                      // global stage counter (same sequence in both issuers)
-            if (resident) mbar_wait(&bars->w_full, 0);      // every lane waits: the loop below stays warp-uniform
+            if (resident) mbar_wait(&bars->w_full, 0);
             int n_tile_unused, m_tile_unused;
+            const bool by_tile = p.issue_mode == 2;
+            const int stages_per_tile = p.n_slabs * chunks_per_tap;
             for (int q = 0; seq_tile(q, n_tile_unused, m_tile_unused); ++q) {
+                if (by_tile && (q & 1) != me) {
+                    // issue_mode 2: the issuers take alternate TILES.  Consecutive tiles use different accumulators,
+                    // so no ordering between the two threads is needed for reproducible sums (each accumulator is
+                    // fed by one thread in program order), and while one thread sits in a barrier hand-over the
+                    // other one's MMAs keep the pipe busy.  The other thread's ring slots are walked one by one with
+                    // a (non-consuming) wait on each: mbarrier waits only know the phase PARITY, so a thread must
+                    // never look at a barrier more than one phase away from where it last saw it.
+                    for (int i = 0; i < stages_per_tile; ++i) {
+                        mbar_wait(&bars->full[stage], phase);
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    }
+                    g += stages_per_tile;
+                    if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+                    continue;
+                }
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1u);
-                if (tr && lane == 0) trace_ev(tr, 1 + me, 0, q, trn);
+                if (tr_tile && lane == 0) trace_ev(tr_tile, 1 + me, 0, q, trn);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
                 bool first = true;              // first stage of the tile: its first MMA overwrites the accumulator
@@ -255,7 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const uint32_t t1 = static_cast<uint32_t>(p.slab_tap[s][1] * chunks_per_tap) * bchunk_step;
                     const uint32_t t2 = static_cast<uint32_t>(p.slab_tap[s][2] * chunks_per_tap) * bchunk_step;
                     for (int c = 0; c < chunks_per_tap; ++c) {
-                        const bool mine = dual ? ((g & 1) == me) : (me == 0);
+                        const bool mine = by_tile ? true : (dual ? ((g & 1) == me) : (me == 0));
                         if (mine) {
                             mbar_wait(&bars->full[stage], phase);
                             if (tr && lane == 0) trace_ev(tr, 1 + me, 1, g, trn);
@@ -264,7 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 uint32_t spins = 0;
                                 while (*issued < g) { if (++spins > (1u << 28)) __trap(); }
                             }
-                            if (tr && lane == 0) trace_ev(tr, 1 + me, 2, g, trn);
+                            if (tr_iss && lane == 0) trace_ev(tr_iss, 1 + me, 2, g, trn);
                             const uint32_t a_lo = smem_lo + static_cast<uint32_t>(stage) * stage_step;
                             const uint32_t bres = wres_lo + static_cast<uint32_t>(c) * bchunk_step;
                             if (elect_one()) {
@@ -275,20 +303,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                     if (j < n_dy) {
                                         // dy shift = j image rows = j * bw * 128 bytes (1024B-aligned) into the slab
                                         const uint64_t a_desc = desc_base | static_cast<uint64_t>(a_lo + j * dy_step);
-                                        const uint32_t b_lo = resident ? bres + (j == 0 ? t0 : (j == 1 ? t1 : t2))
-                                                                       : a_lo + b_in_stage + j * bchunk_step;
+                                        const uint32_t b_lo =
+                                            FOLD ? wres_lo + static_cast<uint32_t>((j * chunks_per_tap + c) * 3 + (s ? 2 : 0)) * bchunk_step
+                                                 : (resident ? bres + (j == 0 ? t0 : (j == 1 ? t1 : t2))
+                                                             : a_lo + b_in_stage + j * bchunk_step);
                                         const uint64_t b_desc = desc_base | static_cast<uint64_t>(b_lo);
 #pragma unroll
                                         for (int k = 0; k < kChunkK / 16; ++k) {
                                             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 units
-                                            umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
+                                            if (FOLD && s) umma_bf16(d_tmem + p.block_n, a_desc + 2u * k, b_desc + 2u * k, idesc_n64, 1u);
+                                            else umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
                                             accumulate = 1u;
                                         }
                                     }
                                 }
                             }
-                            trace_ev(tr, 1 + me, 3, g, trn);
-                            if (dual) { __threadfence_block(); *issued = g + 1; }     // pass the token
+                            trace_ev(tr_iss, 1 + me, 3, g, trn);
+                            if (dual) { if (!(p.debug & 8192)) __threadfence_block(); *issued = g + 1; }     // pass the token
                             if (cl == 2) umma_commit_mc(&bars->empty[stage], 0x3); else umma_commit(&bars->empty[stage]);
                             trace_ev(tr, 1 + me, 4, g, trn);
                             }
@@ -302,10 +333,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 // acc_full expects one arrival per issuer: after this thread's MMAs retire, or at once if it had none
                 if (elect_one()) {
-                    if (mine_any) umma_commit(&bars->acc_full[acc]); else mbar_arrive(&bars->acc_full[acc]);
+                    if (mine_any) umma_commit(&bars->acc_full[acc]); else if (!by_tile) mbar_arrive(&bars->acc_full[acc]);
                 }
                 __syncwarp();
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else if constexpr (FAST) {
@@ -339,6 +370,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // offset of this thread's pixel inside a (full) tile of the [B,H,W] grid, for row_scale / rnorm_out
         const int row_off = ((r >> (p.bw_shift + p.bh_shift)) * p.H + ((r >> p.bw_shift) & (p.bh - 1))) * p.W + (r & (p.bw - 1));
         const int sw = r & 7;
+        constexpr bool fold3 = FOLD == 3;
+        const bool has_left = (lane & (p.bw - 1)) != 0, has_right = (lane & (p.bw - 1)) != (p.bw - 1);   // FOLD (bw <= 32)
         const int et = threadIdx.x - 96 - grp * kGroupThreads;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -392,14 +425,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             chi[t] = min(nch, clo[t] + per);
         }
         const uint64_t half2 = pk2(0.5f, 0.5f);
-        const int acc = grp;                     // tile sequence number parity == group == accumulator stage
-        uint32_t acc_phase = 0;
+        // tile sequence number q -> accumulator stage q % acc_stages (2 or 4; group g sees stages g, g + 2), phase (q / stages) & 1
+        const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages == 4 ? 2 : 1;
         uint8_t* const buf = staging + grp * stg_bytes;
         float* const gred_a = red_a + grp * kGParts * kTileM;
         float* const gred_b = red_b + grp * kGParts * kTileM;
         int n_tile, m_tile;
         for (int q = grp; seq_tile(q, n_tile, m_tile); q += 2) {
             const bool real_tile = m_tile < p.m_tiles;          // false only for a cluster's phantom tile
+            const int acc = q & acc_mask;
+            const uint32_t acc_phase = static_cast<uint32_t>(q >> acc_shift) & 1u;
             const int n0 = n_tile * p.block_n;
             const int c_lo = n_tile ? clo[1] : clo[0], c_hi = n_tile ? chi[1] : chi[0];
             TileGeo tg = {0, 0, 0};
@@ -420,21 +455,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
             // one thread polls the mbarrier; the other epilogue warps park in a hardware named barrier (16 polling
             // warps slow down every other mbarrier operation of the CTA)
-            if (store_leader) { mbar_wait(&bars->acc_full[acc], acc_phase); trace_ev(tr, 3 + grp, 0, q, trn); }
+            if (store_leader) { mbar_wait(&bars->acc_full[acc], acc_phase); trace_ev(tr_tile, 3 + grp, 0, q, trn); }
             named_bar_sync(bar0 + 3, kGroupThreads);
             if (store_leader) trace_ev(tr, 3 + grp, 1, q, trn);
             tc_fence_after();
             const uint32_t t_row = t_lane + static_cast<uint32_t>(acc * p.acc_stride);
             const bool one_chunk = (c_hi - c_lo) == 1;
+            // 16 accumulator columns of this thread's pixel.  FOLD: the three dx column groups, the outer two taken
+            // from the x-1 / x+1 neighbour's lane (tile rows are whole image rows inside one warp; zero at the border)
+            auto load_chunk = [&](int c, uint64_t (&v)[8]) {
+                __syncwarp();
+                if constexpr (FOLD) {
+                    uint64_t t[8];
+                    [[maybe_unused]] uint64_t u[8];
+                    tmem_ld16x2(t_row + c * 16, t);                       // dx = -1 group
+                    tmem_ld16x2(t_row + p.block_n + c * 16, v);           // dx = 0 group
+                    tmem_ld_wait();
+                    if constexpr (fold3) tmem_ld16x2(t_row + 2 * p.block_n + c * 16, u);   // dx = +1 group, in flight during the shuffles
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint64_t a = __shfl_up_sync(0xffffffffu, static_cast<unsigned long long>(t[j]), 1);
+                        if (has_left) v[j] = fadd2(v[j], a);
+                    }
+                    if constexpr (fold3) {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint64_t b = __shfl_down_sync(0xffffffffu, static_cast<unsigned long long>(u[j]), 1);
+                            if (has_right) v[j] = fadd2(v[j], b);
+                        }
+                    }
+                } else {
+                    tmem_ld16x2(t_row + c * 16, v);
+                    tmem_ld_wait();
+                }
+            };
 
             // ---- pass 1: bias (+ row scale), sum of squares; the first chunk (v0) stays in registers
             uint64_t v0[8];
+            [[maybe_unused]] uint64_t v1[8];     // FOLD: the second chunk stays in registers as well
+            bool have_v1 = false;
+            const bool two_chunks = (c_hi - c_lo) == 2;
             bool released = false;
             if (c_lo < c_hi && !skip) {
                 uint64_t s01 = 0ull, s23 = 0ull;
-                __syncwarp();
-                tmem_ld16x2(t_row + c_lo * 16, v0);
-                tmem_ld_wait();
+                load_chunk(c_lo, v0);
                 {
                     const uint32_t ba = sb_bias + static_cast<uint32_t>(n0 + c_lo * 16) * 4u;
 #pragma unroll
@@ -448,10 +513,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 if (has_norm) {
                     for (int c = c_lo + 1; c < c_hi; ++c) {
-                        __syncwarp();
                         uint64_t v[8];
-                        tmem_ld16x2(t_row + c * 16, v);
-                        tmem_ld_wait();
+                        load_chunk(c, v);
                         const uint32_t ba = sb_bias + static_cast<uint32_t>(n0 + c * 16) * 4u;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -460,14 +523,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             const uint64_t f1 = ffma2(v[2 * j + 1], rs2, bb.y);
                             s01 = ffma2(f0, f0, s01);
                             s23 = ffma2(f1, f1, s23);
+                            if constexpr (FOLD != 0) { v1[2 * j] = f0; v1[2 * j + 1] = f1; }
                         }
                     }
+                    if constexpr (FOLD != 0) have_v1 = two_chunks;     // re-assembling a folded chunk costs TMEM loads + shuffles
                     float a0, a1, a2, a3;
                     upk2(s01, a0, a1);
                     upk2(s23, a2, a3);
                     gred_a[part * kTileM + r] = (a0 + a1) + (a2 + a3);
                 }
-                if (one_chunk) {            // nothing more to read from TMEM: release the accumulator right away
+                if (one_chunk || have_v1) {   // nothing more to read from TMEM: release the accumulator right away
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
@@ -498,10 +563,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (c == c_lo) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = v0[j];
+                } else if (FOLD != 0 && have_v1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = v1[j];
                 } else {
-                    __syncwarp();
-                    tmem_ld16x2(t_row + c * 16, v);
-                    tmem_ld_wait();
+                    load_chunk(c, v);
                     const uint32_t ba = sb_bias + static_cast<uint32_t>(nb) * 4u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -593,7 +659,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 for (int i = 1; i < kGParts; ++i) t += gred_b[i * kTileM + r];
                 p.rnorm_out[tile_pix] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
             }
-            acc_phase ^= 1u;
         }
         if (store_leader) bulk_wait_group<0>();
     } else {
@@ -922,8 +987,10 @@ int conv_trace_read(long long* host, int cap) {
 }
 
 int conv_prepare_attributes() {
-    int r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return r;
 }
 
@@ -951,10 +1018,14 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (p.fast_epilogue) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true>, tmA0, tmA1, tmW, tmOut, p);
+    if (p.fold == 3) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3>, tmA0, tmA1, tmW, tmOut, p);
+    } else if (p.fold == 2) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2>, tmA0, tmA1, tmW, tmOut, p);
+    } else if (p.fast_epilogue) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0>, tmA0, tmA1, tmW, tmOut, p);
     } else {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false>, tmA0, tmA1, tmW, tmOut, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0>, tmA0, tmA1, tmW, tmOut, p);
     }
 }
 

@@ -45,10 +45,18 @@ struct ConvParams {
     int slab_dx[kMaxTaps], slab_p[kMaxTaps], slab_dy0[kMaxTaps];
     int slab_tap[kMaxTaps][3];
     int a_rows;                  // rows (pixels) of one A stage
+    // dx-folded 3x3 mode (C_out = 64, tile spans the full image width, resident weights): ONE slab (dx = 0) per
+    // 64-channel chunk; the three dx taps become three 64-column groups of an N = 192 MMA (weights of (dy, dx=-1|0|+1)
+    // stacked along N), and the epilogue adds the groups shifted by one pixel along x (warp shuffles).  A is fetched
+    // from L2 once instead of three times; fold_dyi/dxi give each tap's position (0..2) in the stacked layout.
+    int fold;                    // 0 off; 3 = all three dx groups folded; 2 = [dx=-1 | dx=0] folded, dx=+1 as its own slab
+    int fold_dyi[kMaxTaps], fold_dxi[kMaxTaps];
     int b_resident;              // 1: the whole weight matrix stays in shared memory for the CTA's lifetime
     int k_chunks;                // taps x 64-channel chunks
     int chunks0, chunks1;        // 64-channel chunks per tap for source 0 / source 1
-    int acc_stride;              // TMEM columns between the two accumulator stages
+    int acc_stride;              // TMEM columns between accumulator stages
+    int acc_stages;              // 2, or 4 with the lean epilogue when 4 accumulators fit in TMEM: the MMA side runs
+                                 // further ahead of the epilogue, hiding the accumulator hand-over latency
     int tmem_cols;               // allocated TMEM columns (power of two >= 32)
     int num_stages;              // smem ring depth
     int staging_bufs;            // 1 or 2 output staging buffers (2 only with the lean epilogue)

@@ -47,3 +47,16 @@ for r in (3, 4):
     print(f"STAT {roles[r]}: accfull->bar {med(interval(r,0,1))} pass1 {med(interval(r,1,2))} barpre {med(interval(r,2,3))} pass2 {med(interval(r,3,4))} barpost {med(interval(r,4,5))}")
     af = [t for _, t in by.get((r, 0), [])]
     print(f"STAT {roles[r]}: per-tile period {med([b - a for a, b in zip(af, af[1:])])}")
+
+ae = [t for _, t in by.get((1, 0), [])]
+print(f"STAT issuerA per-tile period (acc_empty ok): {med([b - a for a, b in zip(ae, ae[1:])])}  tiles {len(ae)}  span {ev[-1][0] - ev[0][0]}")
+
+# hand-over between the two issuers: previous stage's "mma issued" -> this stage's "token ok"
+tok = {}; iss = {}
+for r in (1, 2):
+    for idx, t in by.get((r, 2), []): tok[idx] = t
+    for idx, t in by.get((r, 3), []): iss[idx] = t
+ho = [tok[g] - iss[g - 1] for g in sorted(tok) if g - 1 in iss]
+it = [iss[g] - tok[g] for g in sorted(tok) if g in iss]
+per = [tok[g + 1] - tok[g] for g in sorted(tok) if g + 1 in tok]
+print(f"STAT handover (issued g-1 -> token ok g): {med(ho)}   issue (token ok -> issued): {med(it)}   stage period: {med(per)}")
