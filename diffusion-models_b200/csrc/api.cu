@@ -291,22 +291,38 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
         r = encode_bf16_map(&tmW, a->weight, 2, dims, str, wbox);
         if (r != 0) return r;
     }
-    if (p.tma_store) {
-        unsigned long long dims[5], str[5];
-        const unsigned long long L = a->ld_out, OW = a->OW, OH = a->OH, B = a->B, W = a->W, H = a->H;
-        if (!strided_out) {           // [B,OH,OW,ld] -> (c, x, 1, y, b)
-            dims[0] = a->N; dims[1] = OW; dims[2] = 1; dims[3] = OH; dims[4] = B;
-            str[0] = 1; str[1] = L; str[2] = L * OW; str[3] = L * OW; str[4] = L * OW * OH;
-        } else {                      // [B,2H,2W,N] -> ((px c), x, py, y, b): one sub-pixel phase per launch
-            dims[0] = 2ull * L; dims[1] = W; dims[2] = 2; dims[3] = H; dims[4] = B;
-            str[0] = 1; str[1] = 2ull * L; str[2] = OW * L; str[3] = 2ull * OW * L; str[4] = OH * OW * L;
+    CUtensorMap tmRes;
+    {
+        // output (and residual, which is indexed like the output) as a 5-D map whose box is one staged 64-channel tile
+        auto encode_out = [&](CUtensorMap* tm, const void* base, int ld) -> int {
+            unsigned long long dims[5], str[5];
+            const unsigned long long L = ld, OW = a->OW, OH = a->OH, B = a->B, W = a->W, H = a->H;
+            if (!strided_out) {           // [B,OH,OW,ld] -> (c, x, 1, y, b)
+                dims[0] = a->N; dims[1] = OW; dims[2] = 1; dims[3] = OH; dims[4] = B;
+                str[0] = 1; str[1] = L; str[2] = L * OW; str[3] = L * OW; str[4] = L * OW * OH;
+            } else {                      // [B,2H,2W,N] -> ((px c), x, py, y, b): one sub-pixel phase per launch
+                dims[0] = 2ull * L; dims[1] = W; dims[2] = 2; dims[3] = H; dims[4] = B;
+                str[0] = 1; str[1] = 2ull * L; str[2] = OW * L; str[3] = 2ull * OW * L; str[4] = OH * OW * L;
+            }
+            return encode_bf16_map(tm, base, 5, dims, str, box);
+        };
+        if (p.tma_store) {
+            r = encode_out(&tmOut, a->out, a->ld_out);
+            if (r != 0) return r;
+        } else {
+            tmOut = tmA0;
         }
-        r = encode_bf16_map(&tmOut, a->out, 5, dims, str, box);
-        if (r != 0) return r;
-    } else {
-        tmOut = tmA0;
+        // lean epilogue: the residual tile is TMA-loaded into the staging buffer (needs the output's sub-pixel layout
+        // rule, ld_res == N for strided outputs)
+        p.res_tma = 0;
+        tmRes = tmOut;
+        if (p.fast_epilogue && a->residual != nullptr && (!strided_out || a->ld_res == a->N)) {
+            r = encode_out(&tmRes, a->residual, a->ld_res);
+            if (r != 0) return r;
+            p.res_tma = 1;
+        }
     }
-    ddm::launch_conv(tmA0, tmA1, tmW, tmOut, p, g_num_sms, as_stream(stream));
+    ddm::launch_conv(tmA0, tmA1, tmW, tmOut, tmRes, p, g_num_sms, as_stream(stream));
     return finish(1);
 }
 

@@ -11,6 +11,7 @@ struct alignas(8) ConvBarriers {
     uint64_t empty[8];
     uint64_t acc_full[4];
     uint64_t acc_empty[4];
+    uint64_t res_full[2];        // lean epilogue: residual tile landed in group g's staging buffer
     uint64_t w_full;
     uint32_t tmem_base;
     int issued;                  // MMA issue token: number of pipeline stages whose MMAs have all been issued
@@ -66,7 +67,7 @@ template <int kEpiWarps, bool FAST, int FOLD>
 __global__ void __launch_bounds__(96 + 32 * kEpiWarps, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
-               const __grid_constant__ ConvParams p) {
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ ConvParams p) {
     constexpr int kEpiThreads = 32 * kEpiWarps;
     constexpr int kParts = kEpiWarps / 4;
     extern __shared__ uint8_t smem_raw[];
@@ -102,12 +103,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_init(&bars->acc_empty[a], FAST ? kEpiWarps / 2 : kEpiWarps);   // FAST: one epilogue group per stage
         }
         mbar_init(&bars->w_full, 1);
+        mbar_init(&bars->res_full[0], 1);
+        mbar_init(&bars->res_full[1], 1);
         bars->issued = 0;
         fence_barrier_init();
         prefetch_tmap(&tmA0);
         prefetch_tmap(&tmA1);
         prefetch_tmap(&tmW);
         prefetch_tmap(&tmOut);
+        prefetch_tmap(&tmRes);
     }
     if (warp == 1) {
         tmem_alloc(&bars->tmem_base, static_cast<uint32_t>(p.tmem_cols));
@@ -362,8 +366,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const bool has_act = p.act == 1;
         const bool act_prescaled = has_act && affine;
         const bool res_smem = p.residual != nullptr;
+        const bool res_tma = res_smem && p.res_tma != 0;
+        uint32_t res_phase = 0;
         const bool want_rs = p.row_scale != nullptr, want_rn = p.rnorm_out != nullptr;
-        const bool need_geo = leader_warp || res_smem || want_rs || want_rn;   // who needs the tile's coordinates
+        const bool need_geo = leader_warp || (res_smem && !res_tma) || want_rs || want_rn;   // who needs the tile's coordinates
         const bool skip = (p.debug & 1) != 0;   // profiling: no epilogue math / stores
         const int stg_bytes = kTileM * p.block_n * 2;
         const int tiles_xy = p.tiles_x * p.tiles_y;
@@ -447,7 +453,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (want_rs) { const float rs = __ldg(p.row_scale + tile_pix); rs2 = pk2(rs, rs); }
                 }
             }
-            if (res_smem) {     // the group's previous TMA store must have drained its staging buffer before the fetch
+            if (res_tma) {      // one TMA load per 64-channel group, issued once the previous store has drained the buffer
+                if (store_leader) {
+                    bulk_wait_group_read<0>();
+                    const int groups = (min(p.block_n, p.N - n0) + 63) >> 6;
+                    mbar_arrive_expect_tx(&bars->res_full[grp], static_cast<uint32_t>(groups * kTileM * 128));
+                    for (int g = 0; g < groups; ++g) {
+                        const int ch = n0 + g * 64;
+                        if (p.sy == 2) tma_load_5d(buf + g * (kTileM * 128), &tmRes, &bars->res_full[grp], p.ox * p.ld_res + ch, tg.x0, p.oy, tg.y0, tg.b0);
+                        else tma_load_5d(buf + g * (kTileM * 128), &tmRes, &bars->res_full[grp], ch, tg.x0, 0, tg.y0, tg.b0);
+                    }
+                }
+            } else if (res_smem) {     // the group's previous TMA store must have drained its staging buffer before the fetch
                 if (store_leader) bulk_wait_group_read<0>();
                 named_bar_sync(bar0 + 2, kGroupThreads);
                 fetch_residual(n_tile, m_tile, buf);
@@ -541,7 +558,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             // the staging buffer about to be written must have been drained by its previous TMA store
             if (store_leader && !res_smem) bulk_wait_group_read<0>();
-            if (res_smem) cp_async_wait_all();
+            if (res_tma) { if (store_leader) mbar_wait(&bars->res_full[grp], res_phase); res_phase ^= 1u; }
+            else if (res_smem) cp_async_wait_all();
             if (store_leader) trace_ev(tr, 3 + grp, 2, q, trn);
             named_bar_sync(bar0, kGroupThreads);
             if (store_leader) trace_ev(tr, 3 + grp, 3, q, trn);
@@ -995,7 +1013,7 @@ int conv_prepare_attributes() {
 }
 
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                 const ConvParams& p, int num_sms, cudaStream_t stream) {
+                 const CUtensorMap& tmRes, const ConvParams& p, int num_sms, cudaStream_t stream) {
     int stages = 0;
     const int smem = conv_smem_plan(p, &stages);
     int grid;
@@ -1019,13 +1037,13 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (p.fold == 3) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3>, tmA0, tmA1, tmW, tmOut, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     } else if (p.fold == 2) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2>, tmA0, tmA1, tmW, tmOut, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     } else if (p.fast_epilogue) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0>, tmA0, tmA1, tmW, tmOut, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     } else {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0>, tmA0, tmA1, tmW, tmOut, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     }
 }
 

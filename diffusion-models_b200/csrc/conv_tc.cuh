@@ -75,6 +75,7 @@ struct ConvParams {
     int act;                     // 0 none, 1 SiLU
     const __nv_bfloat16* residual;  // added after the activation, indexed like `out`
     int ld_res;
+    int res_tma;                 // 1: the lean epilogue TMA-loads the residual tile into the staging buffer (tmRes)
     void* out;
     int out_f32_nchw;            // 0: bf16 [B,OH,OW,ld_out] ; 1: fp32 [B,N,OH,OW]
     int ld_out;
@@ -83,7 +84,7 @@ struct ConvParams {
 };
 
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                 const ConvParams& p, int num_sms, cudaStream_t stream);
+                 const CUtensorMap& tmRes, const ConvParams& p, int num_sms, cudaStream_t stream);
 // shared-memory plan: returns total dynamic bytes and the stage count that fits (0 stages = does not fit)
 int conv_smem_plan(const ConvParams& p, int* num_stages);
 int conv_prepare_attributes();
