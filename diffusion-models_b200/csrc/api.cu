@@ -237,12 +237,12 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             if (st >= 2) { f.num_stages = st; p = f; }
         }
     }
-    // Two MMA issuer threads (conv_tc.cu).  Mode 2, alternate tiles, when both threads' tiles fit in the smem ring at the
-    // same time (few stages per tile): no ordering needed between the threads.  Otherwise mode 1, alternate stages of
+    // Two MMA issuer threads (conv_tc.cu).  Mode 2, alternate tiles, each thread with its own half of the smem ring, when each
+    // half holds a whole tile (both threads' tiles in flight at once): no ordering needed between the threads.  Otherwise mode 1, alternate stages of
     // the same tile in token order.  DDM_CONV_DEBUG & 32: single issuer; & 16384: always mode 1; & 32768: always mode 2.
     {
         const int stages_per_tile = p.n_slabs * (p.chunks0 + p.chunks1);
-        p.issue_mode = (g_conv_debug & 32) ? 0 : ((g_conv_debug & 16384) ? 1 : ((g_conv_debug & 32768) ? 2 : (stages_per_tile < p.num_stages ? 2 : 1)));
+        p.issue_mode = (g_conv_debug & 32) ? 0 : ((g_conv_debug & 16384) ? 1 : ((g_conv_debug & 32768) ? 2 : ((2 * stages_per_tile <= p.num_stages) ? 2 : 1)));
     }
     if (p.fast_epilogue && !(g_conv_debug & 2048)) {      // four accumulator stages where TMEM has room (DDM_CONV_DEBUG & 2048: two)
         const int cols = (p.fold ? p.fold : 1) * p.block_n;
@@ -336,7 +336,7 @@ int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const floa
     if ((Cout % 8) != 0 || !aligned16(out_bf16)) return DDM_E_ALIGNMENT;
     if (B > 65535) return DDM_E_UNSUPPORTED;
     if (ddm::stem_tc_supported(c0 + c1 + c2, Cout, ksize)) {      // tensor-core path (mma.sync implicit GEMM)
-        ddm::launch_stem_tc(in0, c0, in1, c1, in2, c2, weight, bias, out_bf16, B, H, W, Cout, ksize, as_stream(stream));
+        ddm::launch_stem_tc(in0, c0, in1, c1, in2, c2, weight, bias, out_bf16, B, H, W, Cout, ksize, g_num_sms, as_stream(stream));
         return finish(1);
     }
     if (ddm::stem_smem_bytes(c0 + c1 + c2, Cout, ksize) > 200 * 1024) return DDM_E_UNSUPPORTED;

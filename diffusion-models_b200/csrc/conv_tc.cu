@@ -177,10 +177,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     tma_load_2d(wres + slot * plan.b_chunk_bytes, &tmW, &bars->w_full, kc * kChunkK, 0);
                 }
             }
-            int stage = 0;
-            uint32_t phase = 0;
+            // issue_mode 2 splits the ring in two halves, one per issuer thread (tile parity): every mbarrier then has
+            // a single consumer that visits it in lap order, which parity-only waits require.
+            const bool split = p.issue_mode == 2;
+            const int ring_stages = split ? (p.num_stages >> 1) : p.num_stages;
+            int stage_r[2] = {0, 0};
+            uint32_t phase_r[2] = {0u, 0u};
             int n_tile, m_tile;
             for (int q = 0; seq_tile(q, n_tile, m_tile); ++q) {
+                const int ring = split ? (q & 1) : 0;
+                const int base = ring * ring_stages;
+                int stage = stage_r[ring];
+                uint32_t phase = phase_r[ring];
                 const int tx = m_tile % p.tiles_x;
                 const int ty = (m_tile / p.tiles_x) % p.tiles_y;
                 const int tb = m_tile / (p.tiles_x * p.tiles_y);
@@ -189,18 +197,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 for (int s = 0; s < p.n_slabs; ++s) {
                     const int cx = x0 + p.slab_dx[s], cy = y0 + p.slab_dy0[s], cp = p.slab_p[s];
                     for (int c = 0; c < chunks_per_tap; ++c) {
-                        mbar_wait(&bars->empty[stage], phase ^ 1u);
+                        mbar_wait(&bars->empty[base + stage], phase ^ 1u);
                         if (elect_one()) {
                             trace_ev(tr, 0, 0, q, trn);
-                            uint8_t* a_dst = smem + stage * stage_bytes;
+                            uint8_t* a_dst = smem + (base + stage) * stage_bytes;
                             const bool skip_a = (p.debug & 4) != 0;      // profiling: no A traffic
                             const uint32_t tx_bytes = static_cast<uint32_t>(skip_a ? stage_bytes - plan.a_bytes : stage_bytes);
-                            mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
+                            mbar_arrive_expect_tx(&bars->full[base + stage], tx_bytes);
                             if (skip_a) {
                             } else if (c < p.chunks0) {
-                                tma_load_5d(a_dst, &tmA0, &bars->full[stage], c * kChunkK, cx, cp, cy, b0);
+                                tma_load_5d(a_dst, &tmA0, &bars->full[base + stage], c * kChunkK, cx, cp, cy, b0);
                             } else {
-                                tma_load_5d(a_dst, &tmA1, &bars->full[stage], (c - p.chunks0) * kChunkK, cx, cp, cy, b0);
+                                tma_load_5d(a_dst, &tmA1, &bars->full[base + stage], (c - p.chunks0) * kChunkK, cx, cp, cy, b0);
                             }
                             if (!p.b_resident) {
                                 for (int j = 0; j < p.n_dy; ++j) {
@@ -208,19 +216,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                     const int kcol = (p.slab_tap[s][j] * chunks_per_tap + c) * kChunkK;
                                     if (cl == 2) {      // each CTA fetches half of the rows and multicasts them to both
                                         const int half_rows = p.block_n >> 1;
-                                        tma_load_2d_mc(b_dst + cl_rank * half_rows * (kChunkK * 2), &tmW, &bars->full[stage], kcol,
+                                        tma_load_2d_mc(b_dst + cl_rank * half_rows * (kChunkK * 2), &tmW, &bars->full[base + stage], kcol,
                                                        n0 + cl_rank * half_rows, 0x3);
                                     } else {
-                                        tma_load_2d(b_dst, &tmW, &bars->full[stage], kcol, n0);
+                                        tma_load_2d(b_dst, &tmW, &bars->full[base + stage], kcol, n0);
                                     }
                                 }
                             }
                             trace_ev(tr, 0, 1, q, trn);
                         }
                         __syncwarp();
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                        if (++stage == ring_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
+                stage_r[ring] = stage;
+                phase_r[ring] = phase;
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -259,19 +269,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (resident) mbar_wait(&bars->w_full, 0);
             int n_tile_unused, m_tile_unused;
             const bool by_tile = p.issue_mode == 2;
+            const int ring_stages = by_tile ? (p.num_stages >> 1) : p.num_stages;
+            const int ring_base = by_tile ? me * ring_stages : 0;
             const int stages_per_tile = p.n_slabs * chunks_per_tap;
             for (int q = 0; seq_tile(q, n_tile_unused, m_tile_unused); ++q) {
                 if (by_tile && (q & 1) != me) {
                     // issue_mode 2: the issuers take alternate TILES.  Consecutive tiles use different accumulators,
                     // so no ordering between the two threads is needed for reproducible sums (each accumulator is
                     // fed by one thread in program order), and while one thread sits in a barrier hand-over the
-                    // other one's MMAs keep the pipe busy.  The other thread's ring slots are walked one by one with
-                    // a (non-consuming) wait on each: mbarrier waits only know the phase PARITY, so a thread must
-                    // never look at a barrier more than one phase away from where it last saw it.
-                    for (int i = 0; i < stages_per_tile; ++i) {
-                        mbar_wait(&bars->full[stage], phase);
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-                    }
+                    // other one's MMAs keep the pipe busy.  Each thread owns one half of the smem ring: sharing one
+                    // ring would make a thread wait on barriers it last saw several phases ago, and mbarrier waits
+                    // only know the phase parity (both an arithmetic skip and a walk with non-consuming waits were
+                    // tried; they alias / dead-lock when one thread runs a lap ahead of the other).
                     g += stages_per_tile;
                     if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
                     continue;
@@ -289,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     for (int c = 0; c < chunks_per_tap; ++c) {
                         const bool mine = by_tile ? true : (dual ? ((g & 1) == me) : (me == 0));
                         if (mine) {
-                            mbar_wait(&bars->full[stage], phase);
+                            mbar_wait(&bars->full[ring_base + stage], phase);
                             if (tr && lane == 0) trace_ev(tr, 1 + me, 1, g, trn);
                             tc_fence_after();
                             if (dual) {         // wait for the token: every MMA of stage g-1 has been issued
@@ -297,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 while (*issued < g) { if (++spins > (1u << 28)) __trap(); }
                             }
                             if (tr_iss && lane == 0) trace_ev(tr_iss, 1 + me, 2, g, trn);
-                            const uint32_t a_lo = smem_lo + static_cast<uint32_t>(stage) * stage_step;
+                            const uint32_t a_lo = smem_lo + static_cast<uint32_t>(ring_base + stage) * stage_step;
                             const uint32_t bres = wres_lo + static_cast<uint32_t>(c) * bchunk_step;
                             if (elect_one()) {
                             if (do_mma) {
@@ -324,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             }
                             trace_ev(tr_iss, 1 + me, 3, g, trn);
                             if (dual) { if (!(p.debug & 8192)) __threadfence_block(); *issued = g + 1; }     // pass the token
-                            if (cl == 2) umma_commit_mc(&bars->empty[stage], 0x3); else umma_commit(&bars->empty[stage]);
+                            if (cl == 2) umma_commit_mc(&bars->empty[ring_base + stage], 0x3); else umma_commit(&bars->empty[ring_base + stage]);
                             trace_ev(tr, 1 + me, 4, g, trn);
                             }
                             __syncwarp();
@@ -332,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         }
                         first = false;
                         ++g;
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                        if (++stage == ring_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
                 // acc_full expects one arrival per issuer: after this thread's MMAs retire, or at once if it had none

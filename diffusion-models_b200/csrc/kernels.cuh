@@ -30,7 +30,7 @@ void launch_randn(float* x, unsigned long long seed, unsigned long long sid, lon
 bool stem_tc_supported(int Cin, int Cout, int ks);
 int stem_tc_prepare_attributes();
 void launch_stem_tc(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* w, const float* b,
-                    void* out, int B, int H, int W, int Cout, int ks, cudaStream_t s);
+                    void* out, int B, int H, int W, int Cout, int ks, int num_sms, cudaStream_t s);
 
 // linattn_tc.cu
 void launch_linattn32_tc(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int n_mem, cudaStream_t s);

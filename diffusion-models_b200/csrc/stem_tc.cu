@@ -33,7 +33,7 @@ template <int NT>   // NT = C_out / 8 n-tiles (even)
 __global__ void __launch_bounds__(128)
 stem_tc_kernel(const float* __restrict__ in0, int c0, const float* __restrict__ in1, int c1, const float* __restrict__ in2,
                int c2, const float* __restrict__ weight, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-               int H, int W, int ks, int k_pad) {
+               int H, int W, int ks, int k_pad, int tiles_x, int tiles_y, int total_tiles) {
     constexpr int COUT = NT * 8;
     constexpr int WP = COUT + WPAD;
     extern __shared__ __align__(16) uint8_t stem_smem[];
@@ -43,10 +43,11 @@ stem_tc_kernel(const float* __restrict__ in0, int c0, const float* __restrict__ 
     const int PH = TH + ks - 1, PW = TW + ks - 1;
     __nv_bfloat16* w_s = reinterpret_cast<__nv_bfloat16*>(stem_smem);                 // [k_pad][WP]
     int* koff = reinterpret_cast<int*>(w_s + k_pad * WP);                              // [k_pad]
-    __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(koff + k_pad);            // [Cin][PH][PW]
+    int* pidx = koff + k_pad;                                                          // [Cin*PH*PW] packed (src, c, py, px)
+    const int n_patch = Cin * PH * PW;
+    __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(pidx + ((n_patch + 3) & ~3));  // [Cin][PH][PW]
     __nv_bfloat16* o_s = patch + ((Cin * PH * PW + 7) & ~7);                           // [128][WP]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
 
     for (int i = tid; i < k_pad * COUT; i += 128) {
         const int k = i / COUT, n = i - k * COUT;
@@ -61,22 +62,54 @@ stem_tc_kernel(const float* __restrict__ in0, int c0, const float* __restrict__ 
         }
         koff[k] = off;
     }
-    for (int i = tid; i < Cin * PH * PW; i += 128) {
+    // element i of the patch -> (source, channel in source, patch row, patch column), decoded once per CTA
+    for (int i = tid; i < n_patch; i += 128) {
         const int ci = i / (PH * PW);
         const int rem = i - ci * PH * PW;
         const int py = rem / PW, px = rem - py * PW;
-        const int y = y0 + py - pad, x = x0 + px - pad;
-        float v = 0.0f;
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            const float* src;
-            int c, cn;
-            if (ci < c0) { src = in0; c = ci; cn = c0; }
-            else if (ci < c0 + c1) { src = in1; c = ci - c0; cn = c1; }
-            else { src = in2; c = ci - c0 - c1; cn = c2; }
-            v = __ldg(src + ((static_cast<long long>(b) * cn + c) * H + y) * W + x);
-        }
-        patch[i] = __float2bfloat16_rn(v);
+        int src = 0, c = ci;
+        if (ci >= c0 + c1) { src = 2; c = ci - c0 - c1; }
+        else if (ci >= c0) { src = 1; c = ci - c0; }
+        pidx[i] = (src << 24) | (c << 16) | (py << 8) | px;
     }
+    __syncthreads();
+    // persistent CTA: weights and tables are staged once, then the CTA walks its tiles.  The fp32 patch of the NEXT
+    // tile is fetched into registers while the current tile is multiplied (the kernel was bound by that latency).
+    constexpr int PRE = 20;                        // 128 * 20 >= 8 channels x 14 x 22
+    const int iters = (n_patch + 127) / 128;       // host guarantees iters <= PRE
+    float pre[PRE];
+    auto fetch_patch = [&](int tile) {
+        const int b = tile / (tiles_x * tiles_y);
+        const int trem = tile - b * (tiles_x * tiles_y);
+        const int y0 = (trem / tiles_x) * TH, x0 = (trem % tiles_x) * TW;
+#pragma unroll
+        for (int it = 0; it < PRE; ++it) {
+            const int i = tid + it * 128;
+            float v = 0.0f;
+            if (it < iters && i < n_patch) {
+                const int e = pidx[i];
+                const int y = y0 + ((e >> 8) & 0xFF) - pad, x = x0 + (e & 0xFF) - pad;
+                if (y >= 0 && y < H && x >= 0 && x < W) {
+                    const int sel = e >> 24, c = (e >> 16) & 0xFF;
+                    const float* src = sel == 0 ? in0 : (sel == 1 ? in1 : in2);
+                    const int cn = sel == 0 ? c0 : (sel == 1 ? c1 : c2);
+                    v = __ldg(src + ((static_cast<long long>(b) * cn + c) * H + y) * W + x);
+                }
+            }
+            pre[it] = v;
+        }
+    };
+    if (static_cast<int>(blockIdx.x) < total_tiles) fetch_patch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int b = tile / (tiles_x * tiles_y);
+    const int trem = tile - b * (tiles_x * tiles_y);
+    const int y0 = (trem / tiles_x) * TH, x0 = (trem % tiles_x) * TW;
+#pragma unroll
+    for (int it = 0; it < PRE; ++it) {
+        const int i = tid + it * 128;
+        if (it < iters && i < n_patch) patch[i] = __float2bfloat16_rn(pre[it]);
+    }
+    if (tile + static_cast<int>(gridDim.x) < total_tiles) fetch_patch(tile + gridDim.x);
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
@@ -134,18 +167,22 @@ stem_tc_kernel(const float* __restrict__ in0, int c0, const float* __restrict__ 
 #pragma unroll
         for (int c = 0; c < COUT / 8; ++c) dst[c] = src[c];
     }
+    __syncthreads();        // patch / output staging are rewritten by the next tile
+    }
 }
 
 int stem_tc_smem(int Cin, int Cout, int ks, int k_pad) {
     const int PH = TH + ks - 1, PW = TW + ks - 1;
-    return k_pad * (Cout + WPAD) * 2 + k_pad * 4 + ((Cin * PH * PW + 7) & ~7) * 2 + 128 * (Cout + WPAD) * 2;
+    return k_pad * (Cout + WPAD) * 2 + k_pad * 4 + ((Cin * PH * PW + 3) & ~3) * 4 + ((Cin * PH * PW + 7) & ~7) * 2 + 128 * (Cout + WPAD) * 2;
 }
 
 }  // namespace
 
 bool stem_tc_supported(int Cin, int Cout, int ks) {
     const int k_pad = (ks * ks * Cin + 15) / 16 * 16;
-    return (Cout == 32 || Cout == 64 || Cout == 128) && stem_tc_smem(Cin, Cout, ks, k_pad) <= 200 * 1024;
+    const int n_patch = Cin * (TH + ks - 1) * (TW + ks - 1);
+    return (Cout == 32 || Cout == 64 || Cout == 128) && n_patch <= 128 * 20 && Cin < 256 && (TH + ks - 1) < 256 && (TW + ks - 1) < 256 &&
+           stem_tc_smem(Cin, Cout, ks, k_pad) <= 200 * 1024;
 }
 
 int stem_tc_prepare_attributes() {
@@ -156,15 +193,20 @@ int stem_tc_prepare_attributes() {
 }
 
 void launch_stem_tc(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* w, const float* b,
-                    void* out, int B, int H, int W, int Cout, int ks, cudaStream_t s) {
+                    void* out, int B, int H, int W, int Cout, int ks, int num_sms, cudaStream_t s) {
     const int Cin = c0 + c1 + c2;
     const int k_pad = (ks * ks * Cin + 15) / 16 * 16;
-    const dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    const int total = tiles_x * tiles_y * B;
     const int smem = stem_tc_smem(Cin, Cout, ks, k_pad);
+    int per_sm = (220 * 1024) / (smem + 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const int grid = total < num_sms * per_sm ? total : num_sms * per_sm;
     auto* o = reinterpret_cast<__nv_bfloat16*>(out);
-    if (Cout == 32) stem_tc_kernel<4><<<grid, 128, smem, s>>>(in0, c0, in1, c1, in2, c2, w, b, o, H, W, ks, k_pad);
-    else if (Cout == 64) stem_tc_kernel<8><<<grid, 128, smem, s>>>(in0, c0, in1, c1, in2, c2, w, b, o, H, W, ks, k_pad);
-    else stem_tc_kernel<16><<<grid, 128, smem, s>>>(in0, c0, in1, c1, in2, c2, w, b, o, H, W, ks, k_pad);
+    if (Cout == 32) stem_tc_kernel<4><<<grid, 128, smem, s>>>(in0, c0, in1, c1, in2, c2, w, b, o, H, W, ks, k_pad, tiles_x, tiles_y, total);
+    else if (Cout == 64) stem_tc_kernel<8><<<grid, 128, smem, s>>>(in0, c0, in1, c1, in2, c2, w, b, o, H, W, ks, k_pad, tiles_x, tiles_y, total);
+    else stem_tc_kernel<16><<<grid, 128, smem, s>>>(in0, c0, in1, c1, in2, c2, w, b, o, H, W, ks, k_pad, tiles_x, tiles_y, total);
 }
 
 }  // namespace ddm
