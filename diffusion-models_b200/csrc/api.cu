@@ -257,8 +257,9 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.rnorm_out = a->rnorm_out;
     p.debug = g_conv_debug;
     // streamed weights are the dominant L2->SM traffic of the wide/deep layers (every M tile re-reads the whole weight
-    // matrix): pairs of CTAs in a cluster fetch half of each chunk and multicast it (DDM_CONV_DEBUG & 64 disables)
-    p.cluster = (!p.b_resident && p.m_tiles >= 2 && (p.block_n % 16) == 0 && !(g_conv_debug & 64)) ? 2 : 1;
+    // matrix): pairs of CTAs in a cluster can fetch half of each chunk and multicast it.  Measured: no gain (the limit is
+    // each SM's ~42 B/clk TMA ingest, which multicast does not reduce), so it is off unless DDM_CONV_DEBUG & 64 is set.
+    p.cluster = (!p.b_resident && p.m_tiles >= 2 && (p.block_n % 16) == 0 && (g_conv_debug & 64)) ? 2 : 1;
     p.pairs = (p.m_tiles + 1) / 2;
     CUtensorMap tmA0, tmA1, tmW, tmOut;
     const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};

@@ -23,6 +23,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// exp(x - m) as ex2.approx(x * log2e - m * log2e): one FFMA + one MUFU (expf() expands to ~6 instructions with its
+// range handling; the exponentials are ~60 % of this kernel's instruction stream)
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void load_row32(const __nv_bfloat16* p, float (&f)[32]) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
@@ -119,7 +127,7 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     float psum[8];
     float km[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { psum[c] = 0.0f; km[c] = kmax[part * 8 + c]; }
+    for (int c = 0; c < 8; ++c) { psum[c] = 0.0f; km[c] = kmax[part * 8 + c] * kLog2e; }     // pre-scaled by log2(e)
 
     // the next tile's k/v rows are fetched into registers while the current tile is multiplied (global latency
     // was the limiter: 16 warps/SM, long-scoreboard stalls 8 per issue)
@@ -148,7 +156,7 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
                 uint32_t w[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    w[c] = pack_bf16x2(__expf(f[2 * c] - km[2 * c]), __expf(f[2 * c + 1] - km[2 * c + 1]));
+                    w[c] = pack_bf16x2(ex2_approx(fmaf(f[2 * c], kLog2e, -km[2 * c])), ex2_approx(fmaf(f[2 * c + 1], kLog2e, -km[2 * c + 1])));
                     psum[2 * c] += bf16_lo(w[c]);          // normalise with exactly the rounded weights the MMA sees
                     psum[2 * c + 1] += bf16_hi(w[c]);
                 }
@@ -257,8 +265,9 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
             float ssum = 0.0f;
             if (tok < n) {
+                const float ml = m * kLog2e;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) { f[c] = __expf(f[c] - m); ssum += f[c]; }
+                for (int c = 0; c < 8; ++c) { f[c] = ex2_approx(fmaf(f[c], kLog2e, -ml)); ssum += f[c]; }
             }
             ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
             ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
