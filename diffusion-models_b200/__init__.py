@@ -16,7 +16,7 @@ from .text_conditional import TextConditionalDenoisingDiffusion
 from .latent import LatentDiffusion, ImageConditionalLatentDiffusion, TextConditionalLatentDiffusion
 from .ddim_sampler import DDIMSampler
 from .distributed import sample_sharded, shard_bounds, gather_samples
-from . import image_conditional, text_conditional, latent, _lib
+from . import image_conditional, text_conditional, latent, sampling, _lib
 
 __version__ = "0.1.0"
 __all__ = ["Unet", "DenoisingDiffusion", "GaussianDiffusion", "ModelPrediction", "ImageConditionalDenoisingDiffusion",

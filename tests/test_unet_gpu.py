@@ -230,3 +230,29 @@ def test_large_batch_properties():
     assert torch.isfinite(y).all() and y.min().item() >= 0.0 and y.max().item() <= 1.0
     y_small = d.ddim_sample((16, 3, 32, 32), noise=xT[512:528])
     assert rel_l2(y[512:528], y_small) < 1e-6          # same kernels, same per-row arithmetic
+
+
+def test_sampling_script_checkpoint_to_samples(tmp_path):
+    """Caller integration (sampling.py): a checkpoint in the reference's Trainer.save layout -> load_checkpoint ->
+    batched generation equals sampling the source model directly with the same x_T; grid + FID pool files are written."""
+    from diffusion_models_b200 import sampling
+    src_model, _ = build("base", 0, dim=64, dim_mults=(1, 2, 4, 8))
+    src = _diffusion(src_model, sampling_timesteps=3)
+    ema = {"initted": torch.tensor(True), "step": torch.tensor(77)}
+    ema.update({"ema_model." + k: v.detach().cpu().clone() for k, v in src.state_dict().items()})
+    ema.update({"online_model." + k: torch.zeros_like(v).cpu() for k, v in src.state_dict().items()})
+    torch.save({"step": 77, "model": {}, "opt": {}, "ema": ema, "scaler": None, "version": "2.0.0"}, tmp_path / "model-3.pt")
+
+    import diffusion_models_b200 as ddm
+    dst = ddm.DenoisingDiffusion(ddm.Unet(dim=64, dim_mults=(1, 2, 4, 8)), image_size=32, sampling_timesteps=3).cuda()
+    assert sampling.find_milestones(tmp_path) == [3]
+    assert sampling.load_checkpoint(dst, tmp_path / "model-3.pt") == 77
+    xT = torch.randn((6, 3, 32, 32), generator=torch.Generator().manual_seed(11)).cuda()
+    assert torch.equal(dst.ddim_sample((6, 3, 32, 32), noise=xT), src.ddim_sample((6, 3, 32, 32), noise=xT))
+
+    rep = sampling.run(dst, tmp_path, tmp_path / "out", num_samples=9, batch_size=4, ddim_sampling_timesteps=3, num_fid_samples=10)
+    assert rep == [{"milestone": 3, "step": 77, "samples": (9, 3, 32, 32), "fid_samples": (10, 3, 32, 32)}]
+    assert (tmp_path / "out" / "sample-3.png").stat().st_size > 0
+    import numpy as np
+    pool = np.load(tmp_path / "out" / "fid_samples-3.npz")["images"]
+    assert pool.shape == (10, 3, 32, 32) and np.isfinite(pool).all() and pool.min() >= 0.0 and pool.max() <= 1.0
