@@ -177,32 +177,60 @@ rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     const bool live = row < rows;
     const __nv_bfloat16* xr = x + (live ? row : 0) * C;
     float s = 0.0f;
-    if (live) {
-        for (int c = sub * 8; c < C; c += lpr * 8) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + c));
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    // the lane's pieces of the row stay in registers between the two passes (up to 4 x 16 bytes: C <= 1024 at 32 lanes)
+    constexpr int kKeep = 4;
+    uint4 keep[kKeep];
+    auto sumsq = [&](const uint4& u) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float a = bf16_lo(w[j]), b2 = bf16_hi(w[j]);
-                s = fmaf(a, a, fmaf(b2, b2, s));
-            }
+        for (int j = 0; j < 4; ++j) {
+            const float a = bf16_lo(w[j]), b2 = bf16_hi(w[j]);
+            s = fmaf(a, a, fmaf(b2, b2, s));
         }
+    };
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < kKeep; ++i) {
+            const int c = (sub + i * lpr) * 8;
+            if (c < C) { keep[i] = __ldg(reinterpret_cast<const uint4*>(xr + c)); sumsq(keep[i]); }
+        }
+        for (int c = (sub + kKeep * lpr) * 8; c < C; c += lpr * 8) sumsq(__ldg(reinterpret_cast<const uint4*>(xr + c)));
     }
     for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (!live) return;
     const float rinv = (g != nullptr) ? 1.0f / fmaxf(sqrtf(s), 1e-12f) : 1.0f;
     const float* ssr = (ss != nullptr) ? ss + (row / rows_per_batch) * ss_stride : nullptr;
-    for (int c = sub * 8; c < C; c += lpr * 8) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + c));
+    // vector loads of the per-channel parameters need 16-byte aligned rows (C % 8 == 0 is given; check the bases)
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(ssr) | (static_cast<uintptr_t>(C) * 4)) & 15) == 0;
+    auto finish = [&](int c, const uint4& u) {
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
         float f[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { f[2 * j] = bf16_lo(w[j]); f[2 * j + 1] = bf16_hi(w[j]); }
+        float gv[8], sc[8], sh[8];
+        if (vec_ok) {
+            if (g != nullptr) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(g + c)), b2 = __ldg(reinterpret_cast<const float4*>(g + c + 4));
+                gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w; gv[4] = b2.x; gv[5] = b2.y; gv[6] = b2.z; gv[7] = b2.w;
+            }
+            if (ssr != nullptr) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ssr + c)), b2 = __ldg(reinterpret_cast<const float4*>(ssr + c + 4));
+                const float4 d = __ldg(reinterpret_cast<const float4*>(ssr + C + c)), e = __ldg(reinterpret_cast<const float4*>(ssr + C + c + 4));
+                sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b2.x; sc[5] = b2.y; sc[6] = b2.z; sc[7] = b2.w;
+                sh[0] = d.x; sh[1] = d.y; sh[2] = d.z; sh[3] = d.w; sh[4] = e.x; sh[5] = e.y; sh[6] = e.z; sh[7] = e.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (g != nullptr) gv[j] = __ldg(g + c + j);
+                if (ssr != nullptr) { sc[j] = __ldg(ssr + c + j); sh[j] = __ldg(ssr + C + c + j); }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float t = f[j];
-            if (g != nullptr) t = t * rinv * __ldg(g + c + j);
-            if (ssr != nullptr) t = fmaf(t, __ldg(ssr + c + j) + 1.0f, __ldg(ssr + C + c + j));
+            if (g != nullptr) t = t * rinv * gv[j];
+            if (ssr != nullptr) t = fmaf(t, sc[j] + 1.0f, sh[j]);
             if (act == 1) t = __fdividef(t, 1.0f + __expf(-t));
             f[j] = t;
         }
@@ -214,7 +242,13 @@ rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         }
         *reinterpret_cast<uint4*>(out + row * C + c) =
             make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    };
+#pragma unroll
+    for (int i = 0; i < kKeep; ++i) {
+        const int c = (sub + i * lpr) * 8;
+        if (c < C) finish(c, keep[i]);
     }
+    for (int c = (sub + kKeep * lpr) * 8; c < C; c += lpr * 8) finish(c, __ldg(reinterpret_cast<const uint4*>(xr + c)));
 }
 
 // ------------------------------------------------------------------------------------------------ head conv
