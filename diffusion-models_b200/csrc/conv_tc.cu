@@ -585,11 +585,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             float out_sumsq = 0.0f;
             const uint32_t my_row = smem_u32(buf) + static_cast<uint32_t>(r) * 128u;
             for (int c = c_lo; c < c_hi && !skip; ++c) {
-                uint64_t v[8];
+                uint64_t (&v)[8] = v0;          // the first chunk is already there; later chunks overwrite it (no copies)
                 const int nb = n0 + c * 16;
                 if (c == c_lo) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = v0[j];
                 } else if (FOLD != 0 && have_v1) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = v1[j];
