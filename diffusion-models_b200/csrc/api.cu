@@ -109,7 +109,9 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     std::memset(&p, 0, sizeof(p));
     p.B = a->B; p.H = a->H; p.W = a->W;
     // tile box: 128 pixels = bw x bh x bb (powers of two), x fastest
-    p.bw = a->W >= 128 ? 128 : pow2_ceil(a->W);
+    // at most 32 wide: the A slab of a tile is (bh + 2) x bw pixels, so squarer tiles carry less halo through L2
+    // (128x1 tiles re-read every input row 3 times, 32x4 tiles 1.5 times); DDM_CONV_DEBUG & 262144 restores the wide tiles
+    p.bw = (g_conv_debug & 262144) ? (a->W >= 128 ? 128 : pow2_ceil(a->W)) : (a->W >= 32 ? 32 : pow2_ceil(a->W));
     p.bh = pow2_ceil(a->H); if (p.bh > 128 / p.bw) p.bh = 128 / p.bw;
     p.bb = 128 / (p.bw * p.bh);
     p.tiles_x = (a->W + p.bw - 1) / p.bw;
