@@ -227,7 +227,7 @@ def run_ours(args):
         dom = time_dominant_conv(model, B, dev)
         line["roofline"] = {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": dom["tflops"] / pk["bf16_tflops"], "traffic": DOMINANT_DRAM_BYTES if B == 1024 else None,
-                            "traffic_source": "dram__bytes_read+write of this launch in profiles/r01_ncu_full_conv_v9.txt (ncu --set full, B=1024)",
+                            "traffic_source": "dram__bytes_read+write of this launch in profiles/r01_ncu_full_conv_v10.txt (ncu --set full, B=1024)",
                             "algorithmic_bytes": 2 * B * IMAGE * IMAGE * 64 * 2, "peak_source": pk_src + " (burst, kernel timed alone)",
                             "kernel": "conv_tc_kernel", "layer": dom["layer"], "us_per_launch": dom["us"],
                             "whole_step": {"achieved": ach, "peak": pk["bf16_tflops_sustained"], "frac": ach / pk["bf16_tflops_sustained"],
@@ -244,9 +244,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# ncu --set full capture of downs.0.0.block1 at B=1024 (profiles/r01_ncu_full_conv_v9.txt): 134.37 MB read + 89.24 MB written
+# ncu --set full capture of downs.0.0.block1 at B=1024 (profiles/r01_ncu_full_conv_v10.txt): 134.37 MB read + 90.12 MB written
 # (the tail of the 134 MB output is still in L2 when the kernel ends)
-DOMINANT_DRAM_BYTES = 134367744 + 89242112
+DOMINANT_DRAM_BYTES = 134366208 + 90123264
 
 
 def time_dominant_conv(model, B, dev, reps=20):
