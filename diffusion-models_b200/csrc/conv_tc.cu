@@ -445,6 +445,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint8_t* const buf = staging + grp * stg_bytes;
         float* const gred_a = red_a + grp * kGParts * kTileM;
         float* const gred_b = red_b + grp * kGParts * kTileM;
+        // measured: pays for the dx-folded kernels (-6 %), neutral or worse elsewhere (with two accumulator stages it
+        // serialises the next tile's MMA with this tile's store)
+        const bool merge_acc = FOLD != 0 && p.acc_stages == 4 && (p.debug & 1048576) == 0;
+        bool acc_ready = false;
         int n_tile, m_tile;
         for (int q = grp; seq_tile(q, n_tile, m_tile); q += 2) {
             const bool real_tile = m_tile < p.m_tiles;          // false only for a cluster's phantom tile
@@ -479,10 +483,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 fetch_residual(n_tile, m_tile, buf);
             }
 
-            // one thread polls the mbarrier; the other epilogue warps park in a hardware named barrier (16 polling
-            // warps slow down every other mbarrier operation of the CTA)
-            if (store_leader) { mbar_wait(&bars->acc_full[acc], acc_phase); trace_ev(tr_tile, 3 + grp, 0, q, trn); }
-            named_bar_sync(bar0 + 3, kGroupThreads);
+            // The leader polls the accumulator's mbarrier and the group learns of it through a named barrier (16 polling
+            // warps slow down every other mbarrier operation of the CTA).  From the second tile on, that barrier is the
+            // previous tile's store barrier: the leader waits for the NEXT accumulator just before it (see below).
+            if (!acc_ready) {
+                if (store_leader) { mbar_wait(&bars->acc_full[acc], acc_phase); trace_ev(tr_tile, 3 + grp, 0, q, trn); }
+                named_bar_sync(bar0 + 3, kGroupThreads);
+            }
             if (store_leader) trace_ev(tr, 3 + grp, 1, q, trn);
             tc_fence_after();
             const uint32_t t_row = t_lane + static_cast<uint32_t>(acc * p.acc_stride);
@@ -662,6 +669,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (want_rn) gred_b[part * kTileM + r] = out_sumsq;
             fence_proxy_async();
             if (store_leader) trace_ev(tr, 3 + grp, 4, q, trn);
+            {   // one barrier less per tile: the store barrier also publishes "the group's next accumulator is full"
+                int n_next, m_next;
+                acc_ready = merge_acc && seq_tile(q + 2, n_next, m_next);
+                if (acc_ready && store_leader) {
+                    const int qn = q + 2;
+                    mbar_wait(&bars->acc_full[qn & acc_mask], static_cast<uint32_t>(qn >> acc_shift) & 1u);
+                }
+            }
             named_bar_sync(bar0 + 1, kGroupThreads);
             if (store_leader) trace_ev(tr, 3 + grp, 5, q, trn);
             if (store_leader) {
