@@ -301,14 +301,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             mbar_wait(&bars->full[ring_base + stage], phase);
                             if (tr && lane == 0) trace_ev(tr, 1 + me, 1, g, trn);
                             tc_fence_after();
-                            if (dual) {         // wait for the token: every MMA of stage g-1 has been issued
-                                uint32_t spins = 0;
-                                while (*issued < g) { if (++spins > (1u << 28)) __trap(); }
-                            }
                             if (tr_iss && lane == 0) trace_ev(tr_iss, 1 + me, 2, g, trn);
                             const uint32_t a_lo = smem_lo + static_cast<uint32_t>(ring_base + stage) * stage_step;
                             const uint32_t bres = wres_lo + static_cast<uint32_t>(c) * bchunk_step;
                             if (elect_one()) {
+                            if (dual) {         // wait for the token: every MMA of stage g-1 has been issued.  Polled by the
+                                uint32_t spins = 0;     // issuing lane itself, with everything else already set up
+                                while (*issued < g) { if (++spins > (1u << 28)) __trap(); }
+                            }
                             if (do_mma) {
                                 uint32_t accumulate = first ? 0u : 1u;
 #pragma unroll
