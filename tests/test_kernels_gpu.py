@@ -116,6 +116,37 @@ def test_conv3x3_block_epilogue(lib, B, H, W, Cin, Cout):
     close(rn, ref_rn, 2e-2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,with_res,with_norm", [
+    (5, 32, 32, 64, 64, False, True),      # dx-folded kernel (C_out = 64, tile = whole rows, no residual), 2-issuer tile mode
+    (3, 16, 16, 64, 64, False, True),      # folded, two image rows per warp
+    (2, 10, 32, 64, 64, False, True),      # folded, ragged tile rows (H % 4 != 0)
+    (2, 32, 32, 64, 64, False, False),     # folded, plain conv (no norm / activation)
+    (2, 10, 32, 64, 64, True, True),       # lean kernel, residual tile by TMA, ragged rows
+    (3, 32, 32, 128, 64, True, True),      # 2 chunks per tap, residual
+    (1, 8, 64, 64, 64, True, True),        # 64 wide: two 32-wide tiles per row, taps cross the tile edge
+    (2, 6, 48, 64, 64, True, True),        # 48 wide: second tile half outside the image, ragged rows
+    (1, 4, 160, 32, 64, False, True),      # 160 wide, C_in = 32 (half-filled K chunk)
+])
+def test_conv3x3_lean_kernel_variants(lib, B, H, W, Cin, Cout, with_res, with_norm):
+    """The lean epilogue kernel's variants (dx-folded / residual by TMA / 32-wide tiles) with the batch-shared
+    scale/shift row the sampler uses (Block.forward dd:113-122, ResnetBlock dd:136-148)."""
+    from diffusion_models_b200.packing import pack_conv
+    x = dev(rnd((B, H, W, Cin), 23), BF)
+    pk = pack_conv(rnd((Cout, Cin, 3, 3), 24, (Cin * 9) ** -0.5))
+    kw = dict(bias=dev(rnd((Cout,), 25, 0.1)))
+    if with_norm:
+        kw.update(norm_g=dev(1 + 0.1 * rnd((Cout,), 26)) * Cout ** 0.5, scale_shift=dev(rnd((1, 2 * Cout), 27, 0.3)), act=1)
+    if with_res:
+        kw.update(residual=dev(rnd((B, H, W, Cout), 28), BF))
+    out = torch.zeros((B, H, W, Cout), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (B, H, W), out, **kw)
+    close(out, ref)
+    # the same launch twice gives the same bits (two MMA issuer threads must not make the sums order-dependent)
+    out2 = torch.zeros_like(out)
+    run_conv(lib, [x], pk, (B, H, W), out2, **kw)
+    assert torch.equal(out, out2)
+
+
 def test_conv3x3_shared_scale_shift_row(lib):
     from diffusion_models_b200.packing import pack_conv
     B, H, W, Cin, Cout = 2, 16, 16, 64, 64
@@ -218,10 +249,11 @@ def test_conv_persistent_many_tiles(lib):
 
 
 # ------------------------------------------------------------------------------------------------ other kernels
-@pytest.mark.parametrize("cs", [(3, 0, 0), (4, 4, 0), (3, 3, 2)])
-def test_stem_conv(lib, cs):
+@pytest.mark.parametrize("cs,B", [((3, 0, 0), 2), ((4, 4, 0), 2), ((3, 3, 2), 2), ((3, 0, 0), 96)])
+def test_stem_conv(lib, cs, B):
+    """B = 96: 1440 tiles > the persistent grid, so every CTA walks several tiles with the next patch prefetched."""
     from diffusion_models_b200.packing import pack_stem
-    B, H, W, Co = 2, 32, 40, 64
+    H, W, Co = 32, 40, 64
     ins = [dev(rnd((B, c, H, W), 90 + i)) for i, c in enumerate(cs) if c]
     cin = sum(cs)
     wt = rnd((Co, cin, 7, 7), 95, (cin * 49) ** -0.5)
