@@ -157,8 +157,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         } else {
             const int t = static_cast<int>(blockIdx.x) + q * static_cast<int>(gridDim.x);
             if (t >= p.total_tiles) return false;
-            n_tile = t >= p.m_tiles ? 1 : 0;
-            m_tile = t - n_tile * p.m_tiles;
+            // N tile fastest: the (at most two) N tiles of an M tile run at the same time on neighbouring CTAs, so the
+            // activations are fetched from HBM once and from L2 the second time (C_out = 384: 12 % of the traffic)
+            if (p.n_tiles == 2) { m_tile = t >> 1; n_tile = t & 1; }
+            else { m_tile = t; n_tile = 0; }
         }
         return true;
     };
