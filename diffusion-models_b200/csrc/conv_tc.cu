@@ -29,7 +29,7 @@ __device__ __forceinline__ void trace_ev(bool on, int role, int ev, int idx, int
 }
 
 constexpr int kMaxParts = 4;                       // column parts per accumulator row (epilogue warps / 4)
-constexpr int kBarPre = 1, kBarPost = 2, kBarRes = 3, kBarAcc = 4;   // named barriers of the epilogue warps
+constexpr int kBarPre = 1, kBarPost = 2, kBarRes = 3;   // named barriers of the generic epilogue's warps
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2 : one MUFU op per element
 __device__ __forceinline__ float silu_f(float v) {

@@ -63,8 +63,16 @@ struct ConvParams {
     int fast_epilogue;           // 1: lean epilogue kernel (see conv_tc.cu), chosen by the host when its preconditions hold
     int cluster;                 // 1, or 2: CTA pairs share the (streamed) weight chunks through TMA multicast
     int pairs;                   // ceil(m_tiles / 2) when cluster == 2
-    int issue_mode;              // 0: one MMA issuer thread; 1: two issuers alternating pipeline stages in token order
-    int debug;                   // profiling only (DDM_CONV_DEBUG): 1 = skip epilogue work, 2 = skip MMA issue, 4 = skip A loads
+    int issue_mode;              // 0: one MMA issuer thread; 1: two issuers alternating pipeline stages in token order;
+                                 // 2: two issuers alternating tiles, each with its own half of the smem ring
+    int debug;                   // profiling / bisection only (env DDM_CONV_DEBUG, read once in ddm_init); bits:
+                                 //   1 skip epilogue work      2 skip MMA issue        4 skip A loads
+                                 //   8 generic epilogue only   32 single MMA issuer    64 2-CTA weight multicast ON
+                                 //   128 device-side event trace of CTA 0 (ddm_debug_conv_trace)   256 per-tile events only
+                                 //   512 no dx-folding   1024 3-group folding   2048 two accumulator stages   4096 issuer events only
+                                 //   8192 no fence before the issuer token     16384 / 32768 force issuer mode 1 / 2
+                                 //   262144 wide (128 x 1) tiles   1048576 no merged accumulator barrier in the folded kernels
+                                 // the product path runs with 0
     int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)
     // epilogue
     const float* bias;           // [N] or null
