@@ -223,7 +223,7 @@ class DenoisingDiffusion(nn.Module):
     # ------------------------------------------------------------------ the fused loop
     @torch.no_grad()
     def _run_loop(self, kind: int, shape, times: Sequence[int], coefs: torch.Tensor, *, x_T=None, step_noise=None,
-                  return_all_timesteps=False, use_graph=True, cond=None, text_emb=None, trace=None):
+                  return_all_timesteps=False, use_graph=True, cond=None, text_emb=None, trace=None, raw=False):
         """Shared DDIM / DDPM driver: [select scale-shift row -> U-Net plan -> fused update] per step."""
         dev = self.device
         if dev.type != "cuda":
@@ -333,7 +333,7 @@ class DenoisingDiffusion(nn.Module):
             self._last_graph_launches = loop["per_step"] * S      # kernels launched by replays (not via the C-ABI counter)
         ret = eng.x.clone() if imgs is None else torch.stack(imgs, dim=1)
         out = torch.empty_like(ret)
-        _lib.check(lib.ddm_finalize(ret.data_ptr(), out.data_ptr(), 1 if self._auto_normalize else 0, ret.numel(),
+        _lib.check(lib.ddm_finalize(ret.data_ptr(), out.data_ptr(), 1 if (self._auto_normalize and not raw) else 0, ret.numel(),
                                     torch.cuda.current_stream(dev).cuda_stream))
         return out
 
@@ -363,6 +363,29 @@ class DenoisingDiffusion(nn.Module):
         return self._run_loop(_KIND_DDIM, tuple(shape), [t for t, _ in pairs], self._ddim_coefs(pairs, self.ddim_sampling_eta),
                               x_T=noise, step_noise=step_noise, return_all_timesteps=return_all_timesteps,
                               use_graph=use_graph, trace=trace)
+
+    @torch.no_grad()
+    def q_sample(self, x_start, t, noise=None):
+        """dd:805-821 (forward process; elementwise glue outside the sampling loop)."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        shape = (x_start.shape[0],) + (1,) * (x_start.ndim - 1)
+        a = self.sqrt_alphas_cumprod.gather(-1, t).reshape(shape)
+        b = self.sqrt_one_minus_alphas_cumprod.gather(-1, t).reshape(shape)
+        return a * x_start + b * noise
+
+    @torch.no_grad()
+    def interpolate(self, x1, x2, t=None, lam=0.5, *, q_noise=None, step_noise=None, use_graph=True):
+        """dd:785-803: both images noised to step `t`, blended with weight `lam`, then ancestral steps t-1 .. 0 on the
+        B200 path.  Like the reference, inputs are taken as already normalised and the result is returned raw.
+        Keyword-only extras: `q_noise` = (noise for x1, noise for x2), `step_noise` = per-step draws (parity mode)."""
+        assert x1.shape == x2.shape
+        t = self.num_timesteps - 1 if t is None else int(t)
+        tb = torch.full((x1.shape[0],), t, device=x1.device, dtype=torch.long)
+        n1, n2 = (None, None) if q_noise is None else q_noise
+        img = (1 - lam) * self.q_sample(x1, tb, n1) + lam * self.q_sample(x2, tb, n2)
+        times = list(reversed(range(0, t)))
+        return self._run_loop(_KIND_DDPM, tuple(img.shape), times, self._ddpm_coefs(times), x_T=img.float().contiguous(),
+                              step_noise=step_noise, use_graph=use_graph, raw=True)
 
     @torch.no_grad()
     def sample(self, batch_size=16, return_all_timesteps=False, **kw):

@@ -172,3 +172,24 @@ def p_sample_loop(model: ModelFn, sch: Schedule, x_T: Tensor, *, noises: Optiona
         imgs.append(img)
     ret = img if not return_all_timesteps else torch.stack(imgs, dim=1)
     return (ret + 1) * 0.5 if unnormalize else ret                    # dd:663
+
+
+def q_sample(sch: Schedule, x_start: Tensor, t: int, noise: Tensor) -> Tensor:
+    """dd:805-821 (forward process at a single timestep shared by the batch)."""
+    return sch.sqrt_alphas_cumprod[t] * x_start + sch.sqrt_one_minus_alphas_cumprod[t] * noise
+
+
+def interpolate(model: ModelFn, sch: Schedule, x1: Tensor, x2: Tensor, t: Optional[int] = None, lam: float = 0.5, *,
+                q_noise: Sequence[Tensor], noises: Optional[Sequence[Tensor]] = None, objective="pred_noise",
+                self_condition=False) -> Tensor:
+    """dd:785-803: noise both images to step t, blend, denoise with the ancestral sampler from t-1 down to 0.
+    Returns the raw image (the reference does not unnormalise here).  `noises[i]` = draw of loop iteration i."""
+    t = sch.num_timesteps - 1 if t is None else t
+    img = (1 - lam) * q_sample(sch, x1, t, q_noise[0]) + lam * q_sample(sch, x2, t, q_noise[1])
+    x0 = None
+    for i, s in enumerate(reversed(range(0, t))):
+        tb = torch.full((img.shape[0],), s, dtype=torch.long, device=img.device)
+        out = model(img, tb, x0 if self_condition else None)
+        z = noises[i] if (noises is not None and s > 0) else None
+        img, x0 = ddpm_update(sch, out, img, s, z, objective)
+    return img

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import (unet_forward, infer_config, synth_state_dict, make_schedule, ddim_time_pairs,
-                    ddim_sample, p_sample_loop)
+                    ddim_sample, p_sample_loop, interpolate)
 from conftest import GOLDEN
 
 with open(os.path.join(GOLDEN, "manifest.json")) as f:
@@ -86,6 +86,14 @@ def test_ddim_eta1_all_timesteps(golden):
 def test_ddpm_loop(golden):
     g = golden("ddpm_T6")
     y = p_sample_loop(_model(), make_schedule(6, "cosine"), g["x_T"], noises=list(g["noises"]))
+    _close(y, g["y"], 1e-3)
+
+
+@torch.inference_mode()
+def test_interpolate(golden):
+    g = golden("interpolate_T6")          # dd:785-803: q_sample both, blend, ancestral steps t-1 .. 0, raw output
+    y = interpolate(_model(), make_schedule(6, "cosine"), g["x1"], g["x2"], t=4, lam=0.3, q_noise=list(g["q_noise"]),
+                    noises=list(g["noises"]))
     _close(y, g["y"], 1e-3)
 
 
