@@ -15,10 +15,11 @@ from .image_conditional import ImageConditionalDenoisingDiffusion
 from .text_conditional import TextConditionalDenoisingDiffusion
 from .latent import LatentDiffusion, ImageConditionalLatentDiffusion, TextConditionalLatentDiffusion
 from .ddim_sampler import DDIMSampler
+from .learned_gaussian import LearnedGaussianDiffusion
 from .distributed import sample_sharded, shard_bounds, gather_samples
 from . import image_conditional, text_conditional, latent, sampling, _lib
 
 __version__ = "0.1.0"
 __all__ = ["Unet", "DenoisingDiffusion", "GaussianDiffusion", "ModelPrediction", "ImageConditionalDenoisingDiffusion",
            "TextConditionalDenoisingDiffusion", "LatentDiffusion", "ImageConditionalLatentDiffusion",
-           "TextConditionalLatentDiffusion", "DDIMSampler", "sample_sharded", "shard_bounds", "gather_samples"]
+           "TextConditionalLatentDiffusion", "DDIMSampler", "LearnedGaussianDiffusion", "sample_sharded", "shard_bounds", "gather_samples"]

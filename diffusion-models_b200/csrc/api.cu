@@ -419,6 +419,17 @@ int ddm_sampler_step(int kind, float* x, const float* model_out, const float* no
     return finish(advance ? 2 : 1);
 }
 
+int ddm_sampler_step_learned(float* x, const float* model_out, const float* noise, long long noise_step_stride, float* x_start_out,
+                             const float* coef, int* step_counter, int advance, unsigned long long seed, long long numel,
+                             long long per_sample, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (x == nullptr || model_out == nullptr || coef == nullptr || step_counter == nullptr) return DDM_E_BAD_ARGUMENT;
+    if (numel < 1 || per_sample < 1 || (numel % per_sample) != 0) return DDM_E_BAD_ARGUMENT;
+    ddm::launch_sampler_step_learned(x, model_out, noise, noise_step_stride, x_start_out, coef, step_counter, advance, seed, numel,
+                                     per_sample, as_stream(stream));
+    return finish(advance ? 2 : 1);
+}
+
 int ddm_finalize(const float* x, float* y, int unnormalize, long long numel, void* stream) {
     if (!g_ready) return DDM_E_NOT_INITIALISED;
     ddm::launch_finalize(x, y, unnormalize, numel, as_stream(stream));

@@ -389,6 +389,44 @@ sampler_step_kernel(int kind, float* __restrict__ x, const float* __restrict__ m
     }
 }
 
+// Ancestral step of LearnedGaussianDiffusion (learned_gaussian_diffusion.py:91-111 + dd:638-645): the network output has
+// 2C channels per sample, (pred_noise | variance interpolation fraction v in [-1, 1]):
+//   logvar = f * log(beta_t) + (1 - f) * posterior_log_variance_clipped_t,  f = (v + 1) / 2
+//   x_{t-1} = coef1 * clamp(x0) + coef2 * x_t + exp(0.5 * logvar) * z            (z = 0 at t = 0)
+// coef row: { sqrt_recip_acp, sqrt_recipm1_acp, coef1, coef2, noise_on, min_log, max_log, - }
+__global__ void __launch_bounds__(256)
+sampler_step_learned_kernel(float* __restrict__ x, const float* __restrict__ mo, const float* __restrict__ noise_base,
+                            long long noise_stride, float* __restrict__ x0_out, const float* __restrict__ coef_tab,
+                            int* __restrict__ step_counter, unsigned long long seed, long long numel, long long per_sample) {
+    const int step = *step_counter;
+    const float* noise = noise_base != nullptr ? noise_base + static_cast<long long>(step) * noise_stride : nullptr;
+    const float* cf = coef_tab + static_cast<long long>(step) * 8;
+    const float ra = cf[0], rm1 = cf[1], c1 = cf[2], c2 = cf[3], noise_on = cf[4], min_log = cf[5], max_log = cf[6];
+    const long long grp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i0 = grp * 4;
+    if (i0 >= numel) return;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noise_on != 0.0f && noise == nullptr)
+        normal4(seed, (static_cast<unsigned long long>(static_cast<unsigned>(step_counter[1])) << 32) | (static_cast<unsigned long long>(step) + 1ull),
+                static_cast<unsigned long long>(grp), z);
+    for (int j = 0; j < 4 && i0 + j < numel; ++j) {
+        const long long i = i0 + j;
+        const long long b = i / per_sample, r = i - b * per_sample;
+        const float xt = x[i];
+        const float eps = mo[b * 2 * per_sample + r], v = mo[b * 2 * per_sample + per_sample + r];
+        const float x0 = clamp1(__fsub_rn(__fmul_rn(ra, xt), __fmul_rn(rm1, eps)));
+        float xn = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xt));
+        if (noise_on != 0.0f) {
+            const float f = __fmul_rn(__fadd_rn(v, 1.0f), 0.5f);
+            const float logvar = __fadd_rn(__fmul_rn(f, max_log), __fmul_rn(__fsub_rn(1.0f, f), min_log));
+            const float zi = noise != nullptr ? noise[i] : z[j];
+            xn = __fadd_rn(xn, __fmul_rn(expf(__fmul_rn(0.5f, logvar)), zi));
+        }
+        x[i] = xn;
+        if (x0_out != nullptr) x0_out[i] = x0;
+    }
+}
+
 __global__ void bump_counter_kernel(int* c) { *c += 1; }
 
 __global__ void __launch_bounds__(256)
@@ -465,6 +503,12 @@ void launch_sampler_step(int kind, float* x, const float* mo, const float* noise
                          int advance, int objective, unsigned long long seed, long long numel, cudaStream_t s) {
     sampler_step_kernel<<<blocks_for((numel + 3) / 4, 256), 256, 0, s>>>(kind, x, mo, noise, noise_stride, x0_out, coef, step_counter, objective,
                                                                           seed, numel);
+    if (advance) bump_counter_kernel<<<1, 1, 0, s>>>(step_counter);
+}
+void launch_sampler_step_learned(float* x, const float* mo, const float* noise, long long noise_stride, float* x0_out, const float* coef,
+                                 int* step_counter, int advance, unsigned long long seed, long long numel, long long per_sample, cudaStream_t s) {
+    sampler_step_learned_kernel<<<blocks_for((numel + 3) / 4, 256), 256, 0, s>>>(x, mo, noise, noise_stride, x0_out, coef, step_counter, seed,
+                                                                                  numel, per_sample);
     if (advance) bump_counter_kernel<<<1, 1, 0, s>>>(step_counter);
 }
 void launch_finalize(const float* x, float* y, int unnorm, long long numel, cudaStream_t s) {

@@ -294,8 +294,12 @@ class DenoisingDiffusion(nn.Module):
             else:
                 _lib.check(lib.ddm_select_row(ss_table.data_ptr(), counter.data_ptr(), eng.ss.data_ptr(), eng.ss_width, s))
             eng.run_body(s)
-            _lib.check(lib.ddm_sampler_step(kind, eng.x.data_ptr(), eng.out.data_ptr(), noise_ptr, noise_stride, x0_ptr,
-                                            coef_dev.data_ptr(), counter.data_ptr(), 1, obj, seed, numel, s))
+            if kind == _KIND_DDPM_LEARNED:      # eng.out is [B, 2C, H, W] = (pred_noise | variance fraction)
+                _lib.check(lib.ddm_sampler_step_learned(eng.x.data_ptr(), eng.out.data_ptr(), noise_ptr, noise_stride, x0_ptr,
+                                                        coef_dev.data_ptr(), counter.data_ptr(), 1, seed, numel, C * H * W, s))
+            else:
+                _lib.check(lib.ddm_sampler_step(kind, eng.x.data_ptr(), eng.out.data_ptr(), noise_ptr, noise_stride, x0_ptr,
+                                                coef_dev.data_ptr(), counter.data_ptr(), 1, obj, seed, numel, s))
 
         imgs = [x_T] if return_all_timesteps else None
         self._last_graph_launches = 0
@@ -399,6 +403,6 @@ class DenoisingDiffusion(nn.Module):
                                   "train with the reference and load its state_dict here")
 
 
-_KIND_DDIM, _KIND_DDPM = 0, 1
+_KIND_DDIM, _KIND_DDPM, _KIND_DDPM_LEARNED = 0, 1, 2
 
 GaussianDiffusion = DenoisingDiffusion      # upstream lucidrains name

@@ -157,6 +157,14 @@ int ddm_attention(const void* q, int ldq, const void* k, int ldk, const void* v,
 int ddm_sampler_step(int kind, float* x, const float* model_out, const float* noise, long long noise_step_stride,
                      float* x_start_out, const float* coef, int* step_counter, int advance, int objective, unsigned long long seed,
                      long long numel, void* stream);
+/* Ancestral step with a learned variance (learned_gaussian_diffusion.py:91-111 p_mean_variance + dd:638-645 p_sample):
+ * model_out is [B, 2C, H, W] fp32 = (pred_noise | v), v in [-1, 1] interpolates the log-variance between
+ * posterior_log_variance_clipped[t] and log(betas[t]).  per_sample = C*H*W, numel = B*per_sample.
+ *   row : { sqrt_recip_acp[t], sqrt_recipm1_acp[t], coef1[t], coef2[t], t > 0 ? 1 : 0, min_log[t], max_log[t], 0 }
+ * noise / step_counter / advance / seed as in ddm_sampler_step. */
+int ddm_sampler_step_learned(float* x, const float* model_out, const float* noise, long long noise_step_stride, float* x_start_out,
+                             const float* coef, int* step_counter, int advance, unsigned long long seed, long long numel,
+                             long long per_sample, void* stream);
 /* y = (x + 1) * 0.5 (utils.py:48-49) or a plain copy when unnormalize == 0 */
 int ddm_finalize(const float* x, float* y, int unnormalize, long long numel, void* stream);
 /* dst[i] = src[(*step_counter) * row_len + i]: selects the current step's row of a precomputed per-step table */

@@ -193,3 +193,30 @@ def interpolate(model: ModelFn, sch: Schedule, x1: Tensor, x2: Tensor, t: Option
         z = noises[i] if (noises is not None and s > 0) else None
         img, x0 = ddpm_update(sch, out, img, s, z, objective)
     return img
+
+
+def ddpm_update_learned(sch: Schedule, model_out: Tensor, x: Tensor, t: int, noise: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """One ancestral step of LearnedGaussianDiffusion (learned_gaussian_diffusion.py:91-111 + dd:638-645): the network
+    emits 2C channels, (pred_noise | variance interpolation fraction in [-1, 1])."""
+    eps, frac_un = model_out.chunk(2, dim=1)
+    min_log = sch.posterior_log_variance_clipped[t]
+    max_log = torch.log(sch.betas)[t]
+    frac = (frac_un + 1) * 0.5                                          # unnormalize_to_zero_to_one
+    logvar = frac * max_log + (1 - frac) * min_log
+    x0 = (sch.sqrt_recip_alphas_cumprod[t] * x - sch.sqrt_recipm1_alphas_cumprod[t] * eps).clamp(-1.0, 1.0)
+    mean = sch.posterior_mean_coef1[t] * x0 + sch.posterior_mean_coef2[t] * x
+    if t > 0 and noise is not None:
+        return mean + (0.5 * logvar).exp() * noise, x0
+    return mean, x0
+
+
+def p_sample_loop_learned(model: ModelFn, sch: Schedule, x_T: Tensor, *, noises: Optional[Sequence[Tensor]] = None,
+                          unnormalize=True) -> Tensor:
+    """dd:647-664 driven by LearnedGaussianDiffusion.p_mean_variance."""
+    img = x_T
+    for i, t in enumerate(reversed(range(sch.num_timesteps))):
+        tb = torch.full((img.shape[0],), t, dtype=torch.long, device=img.device)
+        out = model(img, tb, None)
+        z = noises[i] if (noises is not None and t > 0) else None
+        img, _ = ddpm_update_learned(sch, out, img, t, z)
+    return (img + 1) * 0.5 if unnormalize else img

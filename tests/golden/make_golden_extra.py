@@ -25,6 +25,22 @@ def main():
     save("interpolate_T6", x1=x1, x2=x2, y=y, q_noise=torch.stack(cap.draws[:2]), noises=torch.stack(cap.draws[2:]))
     print("draws", len(cap.draws))
 
+    # LearnedGaussianDiffusion (learned_gaussian_diffusion.py:60-111): ancestral sampling with the interpolated
+    # log-variance.  (Its model_predictions / DDIM path references undefined names upstream and cannot run.)
+    import denoising_diffusion.learned_gaussian_diffusion as lg
+    lv = dd.Unet(dim=64, dim_mults=(1, 2, 4, 8), learned_variance=True)
+    shapes = load_synth(lv, 12)
+    ld = lg.LearnedGaussianDiffusion(lv, image_size=32, timesteps=6, beta_schedule="cosine")
+    torch.manual_seed(1234)
+    with CaptureRandn() as cap:
+        y = ld.p_sample_loop((2, 3, 32, 32))
+    save("learned_var_T6", y=y, x_T=cap.draws[0], noises=torch.stack(cap.draws[1:]))
+    x, t = rnd((2, 3, 32, 32), 83), torch.tensor([5, 1])
+    save("unet_learned_var_32", x=x, t=t, y=lv(x, t))
+    import json
+    with open(os.path.join(HERE, "manifest_extra.json"), "w") as f:
+        json.dump({"unet_learned_var_32": {k: list(v) for k, v in shapes.items()}}, f, indent=0, sort_keys=True)
+
 
 if __name__ == "__main__":
     main()

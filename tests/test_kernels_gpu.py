@@ -332,6 +332,32 @@ def test_sampler_step_bit_exact(lib, kind, objective):
     assert counter.item() == 3
 
 
+def test_sampler_step_learned_variance(lib):
+    """LearnedGaussianDiffusion ancestral step (lgd:91-111, dd:638-645) against the same chain of torch fp32 ops."""
+    B, C_, H, W = 2, 3, 16, 16
+    shape = (B, C_, H, W)
+    x, mo, z = dev(rnd(shape, 150)), dev(rnd((B, 2 * C_, H, W), 151)), dev(rnd((3,) + shape, 152))
+    coef = torch.tensor([[1.9, 1.6, 0.7, 0.6, 1.0, -4.0, -1.5, 0.0],
+                         [1.2, 0.66, 0.9, 0.4, 1.0, -6.0, -3.0, 0.0],
+                         [1.01, 0.14, 1.0, 0.0, 0.0, -46.0, -9.0, 0.0]], device="cuda")
+    counter = torch.zeros((2,), dtype=torch.int32, device="cuda")
+    xs, x0 = x.clone(), torch.zeros_like(x)
+    ref = x.clone()
+    for s in range(3):
+        check(lib.ddm_sampler_step_learned(xs.data_ptr(), mo.data_ptr(), z.data_ptr(), x.numel(), x0.data_ptr(), coef.data_ptr(),
+                                           counter.data_ptr(), 1, 0, x.numel(), C_ * H * W, stream()))
+        ra, rm1, c1, c2, on, lo, hi = (coef[s, i] for i in range(7))
+        eps, v = mo.chunk(2, dim=1)
+        frac = (v + 1) * 0.5
+        logvar = frac * hi + (1 - frac) * lo
+        r0 = (ra * ref - rm1 * eps).clamp(-1.0, 1.0)
+        mean = c1 * r0 + c2 * ref
+        ref = mean + (0.5 * logvar).exp() * z[s] if on.item() != 0 else mean
+        assert torch.equal(x0, r0)
+        assert (xs - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())     # exp() may differ in the last ulp
+    assert counter[0].item() == 3
+
+
 def test_philox_normal_statistics(lib):
     n = 1 << 20
     x = torch.zeros((n,), device="cuda")

@@ -8,11 +8,13 @@ import pytest
 import torch
 
 from oracle import (unet_forward, infer_config, synth_state_dict, make_schedule, ddim_time_pairs,
-                    ddim_sample, p_sample_loop, interpolate)
+                    ddim_sample, p_sample_loop, interpolate, p_sample_loop_learned)
 from conftest import GOLDEN
 
 with open(os.path.join(GOLDEN, "manifest.json")) as f:
     MANIFEST = json.load(f)
+with open(os.path.join(GOLDEN, "manifest_extra.json")) as f:          # tests/golden/make_golden_extra.py
+    MANIFEST.update(json.load(f))
 
 UNET_CASES = {
     # name: (seed, infer_config kwargs)
@@ -86,6 +88,21 @@ def test_ddim_eta1_all_timesteps(golden):
 def test_ddpm_loop(golden):
     g = golden("ddpm_T6")
     y = p_sample_loop(_model(), make_schedule(6, "cosine"), g["x_T"], noises=list(g["noises"]))
+    _close(y, g["y"], 1e-3)
+
+
+@torch.inference_mode()
+def test_learned_variance(golden):
+    # Unet(learned_variance=True): 2C output channels; LearnedGaussianDiffusion ancestral loop (lgd:91-111)
+    sd = synth_state_dict(MANIFEST["unet_learned_var_32"], 12)
+    cfg = infer_config(sd)
+    g = golden("unet_learned_var_32")
+    y = unet_forward(sd, g["x"], g["t"], cfg)
+    assert y.shape == (2, 6, 32, 32)
+    _close(y, g["y"])
+    g = golden("learned_var_T6")
+    model = lambda x, t, sc: unet_forward(sd, x, t, cfg)
+    y = p_sample_loop_learned(model, make_schedule(6, "cosine"), g["x_T"], noises=list(g["noises"]))
     _close(y, g["y"], 1e-3)
 
 

@@ -166,6 +166,23 @@ def test_interpolate_vs_reference(golden):
     assert y.min().item() < 0.0          # raw output: the reference does not unnormalise here
 
 
+def test_learned_variance_vs_reference(golden):
+    """Unet(learned_variance=True) forward and LearnedGaussianDiffusion.p_sample_loop against the reference fixtures."""
+    import diffusion_models_b200 as ddm
+    model, _ = build("base", 12, dim=64, dim_mults=(1, 2, 4, 8), learned_variance=True)
+    g = golden("unet_learned_var_32")
+    y = model(g["x"].cuda(), g["t"].cuda())
+    assert y.shape == (2, 6, 32, 32) and rel_l2(y, g["y"]) < EPS_TOL
+    d = ddm.LearnedGaussianDiffusion(model, image_size=32, timesteps=6, beta_schedule="cosine").cuda()
+    g = golden("learned_var_T6")
+    y = d.p_sample_loop((2, 3, 32, 32), noise=g["x_T"].cuda(), step_noise=g["noises"].cuda())
+    assert rel_l2(y, g["y"]) < FINAL_TOL and (y.cpu() - g["y"]).abs().mean().item() < 1e-2
+    y2 = d.sample(batch_size=2, noise=g["x_T"].cuda(), step_noise=g["noises"].cuda())
+    assert rel_l2(y2, g["y"]) < FINAL_TOL
+    with pytest.raises(NotImplementedError):
+        d.ddim_sample((2, 3, 32, 32))
+
+
 def test_ddim_pred_v_cosine(golden):
     g = golden("ddim_predv_S3")
     model, _ = build("base", 0, dim=64, dim_mults=(1, 2, 4, 8))
