@@ -239,6 +239,24 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             if (st >= 2) { f.num_stages = st; p = f; }
         }
     }
+    // Lean epilogue with four groups of four warps (thread = pixel x all columns; conv_tc.cu) where four accumulator stages
+    // fit: costs two more staging buffers and a second TMEM pass.  Measured (B = 1024, 32x32): -11 % on the 1x1 conv +
+    // RMSNorm + residual of the attention output (to_out), +18 % on 3x3 64->64, +35 % on C_out = 128 -- so it is used
+    // for the first kind only.  DDM_CONV_DEBUG & 4194304 forces it wherever it fits, & 8388608 disables it.
+    p.epi_groups = 2;
+    const bool four_groups_pays = a->ntaps == 1 && a->norm_g != nullptr && a->residual != nullptr && p.block_n == 64;
+    if (p.fast_epilogue && ((g_conv_debug & 4194304) || (four_groups_pays && !(g_conv_debug & 8388608))) && !(g_conv_debug & 2048) &&
+        p.fold != 3) {
+        const int cols = (p.fold ? p.fold : 1) * p.block_n;
+        const int stride = pow2_ceil(cols) < 32 ? 32 : pow2_ceil(cols);
+        if (4 * stride <= 512) {
+            ddm::ConvParams f = p;
+            f.staging_bufs = 4;
+            int st = 0;
+            ddm::conv_smem_plan(f, &st);
+            if (st >= 2) { f.num_stages = st; f.epi_groups = 4; p = f; }
+        }
+    }
     // Two MMA issuer threads (conv_tc.cu).  Mode 2, alternate tiles, each thread with its own half of the smem ring, when each
     // half holds a whole tile (both threads' tiles in flight at once): no ordering needed between the threads.  Otherwise mode 1, alternate stages of
     // the same tile in token order.  DDM_CONV_DEBUG & 32: single issuer; & 16384: always mode 1; & 32768: always mode 2.

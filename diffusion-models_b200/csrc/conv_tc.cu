@@ -11,7 +11,7 @@ struct alignas(8) ConvBarriers {
     uint64_t empty[8];
     uint64_t acc_full[4];
     uint64_t acc_empty[4];
-    uint64_t res_full[2];        // lean epilogue: residual tile landed in group g's staging buffer
+    uint64_t res_full[4];        // lean epilogue: residual tile landed in group g's staging buffer
     uint64_t w_full;
     uint32_t tmem_base;
     int issued;                  // MMA issue token: number of pipeline stages whose MMAs have all been issued
@@ -53,7 +53,7 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
     s.stage_bytes = s.a_bytes + (p.b_resident ? 0 : p.n_dy * s.b_chunk_bytes);
     s.wres_off = num_stages * s.stage_bytes;
     s.staging_off = s.wres_off + (p.b_resident ? p.k_chunks * s.b_chunk_bytes : 0);
-    s.colp_off = s.staging_off + (p.tma_store ? (p.staging_bufs == 2 ? 2 : 1) * kTileM * p.block_n * 2 : 0);
+    s.colp_off = s.staging_off + (p.tma_store ? (p.staging_bufs > 1 ? p.staging_bufs : 1) * kTileM * p.block_n * 2 : 0);
     s.red_off = s.colp_off + 3 * p.n_pad * 4;
     s.bars_off = s.red_off + 2 * kMaxParts * kTileM * 4;
     s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
@@ -63,7 +63,7 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
 // kEpiWarps epilogue warps (multiple of 4).  FAST: lean epilogue for the common case (bf16 output through smem
 // staging + TMA store, full tiles where per-pixel side inputs are used, scale/shift shared by the batch); packed
 // f32x2 arithmetic, all per-pixel address math hoisted out of the tile loop.
-template <int kEpiWarps, bool FAST, int FOLD>
+template <int kEpiWarps, bool FAST, int FOLD, int GROUPS>
 __global__ void __launch_bounds__(96 + 32 * kEpiWarps, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
@@ -100,11 +100,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int a = 0; a < 4; ++a) {
             mbar_init(&bars->acc_full[a], p.issue_mode == 2 ? 1 : 2);   // per issuer thread, or (mode 2) the tile's owner only
-            mbar_init(&bars->acc_empty[a], FAST ? kEpiWarps / 2 : kEpiWarps);   // FAST: one epilogue group per stage
+            mbar_init(&bars->acc_empty[a], FAST ? kEpiWarps / GROUPS : kEpiWarps);   // FAST: one epilogue group per stage
         }
         mbar_init(&bars->w_full, 1);
-        mbar_init(&bars->res_full[0], 1);
-        mbar_init(&bars->res_full[1], 1);
+        for (int g = 0; g < 4; ++g) mbar_init(&bars->res_full[g], 1);
         bars->issued = 0;
         fence_barrier_init();
         prefetch_tmap(&tmA0);
@@ -362,14 +361,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // stays in registers between the norm pass and the store pass, packed f32x2 arithmetic.
         // Two independent epilogue groups of kEpiWarps/2 warps: group g owns accumulator stage g, staging buffer g and
         // its own named barriers, and handles every other tile of this CTA, so two tile epilogues are in flight.
-        constexpr int kGroupWarps = kEpiWarps / 2;
+        // GROUPS = 2: 8 warps per tile (thread = pixel x column half, sums of squares meet in shared memory).
+        // GROUPS = 4: 4 warps per tile (thread = pixel x all columns: no cross-warp reduction, four tiles in flight on
+        // the four accumulator stages, half as many threads per named barrier).
+        constexpr int kGroupWarps = kEpiWarps / GROUPS;
         constexpr int kGroupThreads = 32 * kGroupWarps;
         constexpr int kGParts = kGroupWarps / 4;
         const int grp = (warp - 3) / kGroupWarps;
         const int ew = (warp - 3) - grp * kGroupWarps;
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int part = ew >> 2;               // column part (within the group) handled by this warp
-        const int bar0 = 1 + grp * 4;           // this group's named barriers: bar0 + {0 pre, 1 post, 2 residual, 3 accumulator}
+        const int bar0 = 1 + grp * 3;           // this group's named barriers: bar0 + {0 pre, 1 post, 2 residual / accumulator}
         const int r = q * 32 + lane;            // accumulator row == tile pixel
         const bool leader_warp = (ew == 0);
         const bool store_leader = leader_warp && (lane == 0);
@@ -452,7 +454,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const bool merge_acc = FOLD != 0 && p.acc_stages == 4 && (p.debug & 1048576) == 0;
         bool acc_ready = false;
         int n_tile, m_tile;
-        for (int q = grp; seq_tile(q, n_tile, m_tile); q += 2) {
+        for (int q = grp; seq_tile(q, n_tile, m_tile); q += GROUPS) {
             const bool real_tile = m_tile < p.m_tiles;          // false only for a cluster's phantom tile
             const int acc = q & acc_mask;
             const uint32_t acc_phase = static_cast<uint32_t>(q >> acc_shift) & 1u;
@@ -490,7 +492,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             // previous tile's store barrier: the leader waits for the NEXT accumulator just before it (see below).
             if (!acc_ready) {
                 if (store_leader) { mbar_wait(&bars->acc_full[acc], acc_phase); trace_ev(tr_tile, 3 + grp, 0, q, trn); }
-                named_bar_sync(bar0 + 3, kGroupThreads);
+                named_bar_sync(bar0 + 2, kGroupThreads);
             }
             if (store_leader) trace_ev(tr, 3 + grp, 1, q, trn);
             tc_fence_after();
@@ -673,9 +675,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (store_leader) trace_ev(tr, 3 + grp, 4, q, trn);
             {   // one barrier less per tile: the store barrier also publishes "the group's next accumulator is full"
                 int n_next, m_next;
-                acc_ready = merge_acc && seq_tile(q + 2, n_next, m_next);
+                acc_ready = merge_acc && seq_tile(q + GROUPS, n_next, m_next);
                 if (acc_ready && store_leader) {
-                    const int qn = q + 2;
+                    const int qn = q + GROUPS;
                     mbar_wait(&bars->acc_full[qn & acc_mask], static_cast<uint32_t>(qn >> acc_shift) & 1u);
                 }
             }
@@ -1029,10 +1031,12 @@ int conv_trace_read(long long* host, int cap) {
 }
 
 int conv_prepare_attributes() {
-    int r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return r;
 }
 
@@ -1060,14 +1064,18 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (p.fold == 3) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+    if (p.epi_groups == 4 && p.fold == 2) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 4>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+    } else if (p.epi_groups == 4) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0, 4>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+    } else if (p.fold == 3) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     } else if (p.fold == 2) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     } else if (p.fast_epilogue) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     } else {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     }
 }
 

@@ -59,7 +59,8 @@ struct ConvParams {
                                  // further ahead of the epilogue, hiding the accumulator hand-over latency
     int tmem_cols;               // allocated TMEM columns (power of two >= 32)
     int num_stages;              // smem ring depth
-    int staging_bufs;            // 1 or 2 output staging buffers (2 only with the lean epilogue)
+    int staging_bufs;            // output staging buffers: 1 (generic epilogue) or one per epilogue group (lean epilogue)
+    int epi_groups;              // lean epilogue: 2 groups of 8 warps, or 4 groups of 4 warps (needs 4 accumulator stages)
     int fast_epilogue;           // 1: lean epilogue kernel (see conv_tc.cu), chosen by the host when its preconditions hold
     int cluster;                 // 1, or 2: CTA pairs share the (streamed) weight chunks through TMA multicast
     int pairs;                   // ceil(m_tiles / 2) when cluster == 2
@@ -72,6 +73,7 @@ struct ConvParams {
                                  //   512 no dx-folding   1024 3-group folding   2048 two accumulator stages   4096 issuer events only
                                  //   8192 no fence before the issuer token     16384 / 32768 force issuer mode 1 / 2
                                  //   262144 wide (128 x 1) tiles   1048576 no merged accumulator barrier in the folded kernels
+                                 //   4194304 / 8388608 four epilogue groups everywhere / nowhere
                                  // the product path runs with 0
     int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)
     // epilogue
