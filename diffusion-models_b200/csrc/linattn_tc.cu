@@ -98,11 +98,21 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
         float mx[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) mx[c] = -INFINITY;
-        for (int tok = trow; tok < n; tok += 32) {
-            float f[8];
-            load8(kp + static_cast<long long>(tok) * ld + part * 8, f);
+        // eight independent 16-byte loads in flight per thread (the pass is pure latency otherwise)
+        for (int tok = trow; tok < n; tok += 32 * 8) {
+            uint4 u[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) mx[c] = fmaxf(mx[c], f[c]);
+            for (int i = 0; i < 8; ++i)
+                if (tok + 32 * i < n) u[i] = __ldg(reinterpret_cast<const uint4*>(kp + static_cast<long long>(tok + 32 * i) * ld + part * 8));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (tok + 32 * i < n) {
+                    float f[8];
+                    unpack8(u[i], f);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) mx[c] = fmaxf(mx[c], f[c]);
+                }
+            }
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) red[trow * 33 + part * 8 + c] = mx[c];
