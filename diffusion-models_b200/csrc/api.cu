@@ -125,6 +125,13 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if (a->N_pad > 512) return DDM_E_UNSUPPORTED;
     p.n_tiles = (a->N_pad + 255) / 256;
     p.block_n = ((a->N_pad + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;   // e.g. N=384 -> 2 tiles of 192
+    // C_out = 384 (to_qkv) with one 64-channel K chunk and no fused norm: three tiles of 128 instead of two of 192, so that
+    // four accumulator stages fit in TMEM and the four-group lean epilogue (single pass here) applies.  Measured at
+    // B = 1024: 208 -> 192 us at 32x32, 58.5 -> 55 us at 16x16; with K = 128 the 2 x 192 split stays faster.
+    // DDM_CONV_DEBUG & 16777216 keeps 2 x 192.
+    const bool qkv_three_tiles = a->N_pad == 384 && a->K_pad == 64 && a->norm_g == nullptr && a->rnorm_out == nullptr &&
+                                 a->residual == nullptr && !(g_conv_debug & 16777216);
+    if (qkv_three_tiles) { p.n_tiles = 3; p.block_n = 128; }
     p.total_tiles = p.m_tiles * p.n_tiles;
     p.N = a->N;
     if (a->norm_g != nullptr && p.n_tiles != 1) return DDM_E_UNSUPPORTED;
@@ -244,7 +251,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // RMSNorm + residual of the attention output (to_out), +18 % on 3x3 64->64, +35 % on C_out = 128 -- so it is used
     // for the first kind only.  DDM_CONV_DEBUG & 4194304 forces it wherever it fits, & 8388608 disables it.
     p.epi_groups = 2;
-    const bool four_groups_pays = a->ntaps == 1 && a->norm_g != nullptr && a->residual != nullptr && p.block_n == 64;
+    const bool four_groups_pays = (a->ntaps == 1 && a->norm_g != nullptr && a->residual != nullptr && p.block_n == 64) || qkv_three_tiles;
     if (p.fast_epilogue && ((g_conv_debug & 4194304) || (four_groups_pays && !(g_conv_debug & 8388608))) && !(g_conv_debug & 2048) &&
         p.fold != 3) {
         const int cols = (p.fold ? p.fold : 1) * p.block_n;
@@ -279,7 +286,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // streamed weights are the dominant L2->SM traffic of the wide/deep layers (every M tile re-reads the whole weight
     // matrix): pairs of CTAs in a cluster can fetch half of each chunk and multicast it.  Measured: no gain (the limit is
     // each SM's ~42 B/clk TMA ingest, which multicast does not reduce), so it is off unless DDM_CONV_DEBUG & 64 is set.
-    p.cluster = (!p.b_resident && p.m_tiles >= 2 && (p.block_n % 16) == 0 && (g_conv_debug & 64)) ? 2 : 1;
+    p.cluster = (!p.b_resident && p.m_tiles >= 2 && p.n_tiles <= 2 && (p.block_n % 16) == 0 && (g_conv_debug & 64)) ? 2 : 1;
     p.pairs = (p.m_tiles + 1) / 2;
     CUtensorMap tmA0, tmA1, tmW, tmOut;
     const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};

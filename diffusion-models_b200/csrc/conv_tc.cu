@@ -157,9 +157,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int t = static_cast<int>(blockIdx.x) + q * static_cast<int>(gridDim.x);
             if (t >= p.total_tiles) return false;
             // N tile fastest: the (at most two) N tiles of an M tile run at the same time on neighbouring CTAs, so the
-            // activations are fetched from HBM once and from L2 the second time (C_out = 384: 12 % of the traffic)
-            if (p.n_tiles == 2) { m_tile = t >> 1; n_tile = t & 1; }
-            else { m_tile = t; n_tile = 0; }
+            // activations are fetched from HBM once and from L2 afterwards (C_out = 384: 12 % of the traffic)
+            if (p.n_tiles == 1) { m_tile = t; n_tile = 0; }
+            else if (p.n_tiles == 2) { m_tile = t >> 1; n_tile = t & 1; }
+            else { m_tile = t / p.n_tiles; n_tile = t - m_tile * p.n_tiles; }
         }
         return true;
     };
@@ -433,16 +434,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         };
         // shared-space addresses of the per-column vectors, the reduction scratch and this thread's staging row
         const uint32_t sb_bias = smem_u32(col_bias), sb_mul = smem_u32(col_mul), sb_add = smem_u32(col_add);
-        // chunk range of this thread for each of the (at most two) N tiles
-        int clo[2], chi[2];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int nc = min(p.block_n, p.N - t * p.block_n);
+        // chunk range of this thread inside an N tile (the last tile may be narrower)
+        auto chunk_range = [&](int n_tile, int& lo, int& hi) {
+            const int nc = min(p.block_n, p.N - n_tile * p.block_n);
             const int nch = nc > 0 ? (nc + 15) >> 4 : 0;
             const int per = (nch + kGParts - 1) / kGParts;
-            clo[t] = min(nch, part * per);
-            chi[t] = min(nch, clo[t] + per);
-        }
+            lo = min(nch, part * per);
+            hi = min(nch, lo + per);
+        };
         const uint64_t half2 = pk2(0.5f, 0.5f);
         // tile sequence number q -> accumulator stage q % acc_stages (2 or 4; group g sees stages g, g + 2), phase (q / stages) & 1
         const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages == 4 ? 2 : 1;
@@ -459,7 +458,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int acc = q & acc_mask;
             const uint32_t acc_phase = static_cast<uint32_t>(q >> acc_shift) & 1u;
             const int n0 = n_tile * p.block_n;
-            const int c_lo = n_tile ? clo[1] : clo[0], c_hi = n_tile ? chi[1] : chi[0];
+            int c_lo, c_hi;
+            chunk_range(n_tile, c_lo, c_hi);
             TileGeo tg = {0, 0, 0};
             int tile_pix = 0;
             uint64_t rs2 = pk2(1.0f, 1.0f);
