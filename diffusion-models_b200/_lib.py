@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libddm_b200.so")
-SOURCES = ["conv_tc.cu", "small_kernels.cu", "attention.cu", "linattn_tc.cu", "stem_tc.cu", "api.cu"]
+SOURCES = ["conv_tc.cu", "small_kernels.cu", "attention.cu", "linattn_tc.cu", "linattn_fused.cu", "stem_tc.cu", "api.cu"]
 HEADERS = ["conv_tc.cuh", "kernels.cuh", "ptx.cuh", os.path.join("..", "..", "include", "ddm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
@@ -41,6 +41,17 @@ class ConvArgs(C.Structure):
     ]
 
 
+class LinAttnBlockArgs(C.Structure):
+    """Mirror of `ddm_linattn_block_args` (include/ddm_b200.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("out", C.c_void_p),
+        ("B", C.c_int), ("n", C.c_int), ("C", C.c_int),
+        ("w_qkv", C.c_void_p), ("w_out", C.c_void_p), ("bias_out", C.c_void_p), ("g_out", C.c_void_p),
+        ("mem_kv", C.c_void_p), ("k_shift", C.c_void_p),
+        ("heads", C.c_int), ("dim_head", C.c_int), ("n_mem", C.c_int),
+    ]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "ddm_abi_version": (C.c_int, []),
@@ -61,6 +72,8 @@ EXPORTS = {
                                   C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "ddm_linear_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]),
+    "ddm_linear_attention_block_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ddm_linear_attention_block": (C.c_int, [C.POINTER(LinAttnBlockArgs), C.c_void_p]),
     "ddm_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ddm_sampler_step": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,

@@ -13,6 +13,12 @@
 #include "conv_tc.cuh"
 #include "kernels.cuh"
 
+namespace ddm {
+void launch_linattn_fused(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmWqkv, const CUtensorMap& tmWout,
+                          const float* bias_out, const float* g_out, const float* mem_kv, const float* k_shift, int B, int n, int C,
+                          int n_mem, int num_sms, cudaStream_t s);
+}
+
 namespace {
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
@@ -87,6 +93,8 @@ int ddm_init(int device) {
     r = ddm::stem_prepare_attributes();
     if (r != 0) return r;
     r = ddm::stem_tc_prepare_attributes();
+    if (r != 0) return r;
+    r = ddm::linattn_fused_prepare_attributes();
     if (r != 0) return r;
     if (const char* dbg = std::getenv("DDM_CONV_DEBUG")) g_conv_debug = std::atoi(dbg);   // bottleneck bisection, see conv_tc.cuh
     g_ready = true;
@@ -422,6 +430,45 @@ int ddm_linear_attention(const void* qkv_bf16, const float* mem_kv, void* out_bf
     if (B > 65535 || n_mem < 0 || n_mem > 16 || (n_mem > 0 && mem_kv == nullptr)) return DDM_E_UNSUPPORTED;
     const int r = ddm::launch_linear_attention(qkv_bf16, mem_kv, out_bf16, B, n, heads, d, n_mem, as_stream(stream));
     return r != 0 ? r : finish(1);
+}
+
+int ddm_linear_attention_block_supported(int C, int n, int heads, int dim_head, int n_mem) {
+    return ddm::linattn_fused_supported(C, n, heads, dim_head, n_mem) ? 1 : 0;
+}
+
+int ddm_linear_attention_block(const ddm_linattn_block_args* a, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (a == nullptr || a->x == nullptr || a->out == nullptr || a->w_qkv == nullptr || a->w_out == nullptr || a->bias_out == nullptr ||
+        a->g_out == nullptr || a->k_shift == nullptr || a->B < 1 || (a->n_mem > 0 && a->mem_kv == nullptr) || a->x == a->out)
+        return DDM_E_BAD_ARGUMENT;
+    if (!ddm::linattn_fused_supported(a->C, a->n, a->heads, a->dim_head, a->n_mem)) return DDM_E_UNSUPPORTED;
+    if (static_cast<long long>(a->B) * a->n > 0x7FFFFFFFll) return DDM_E_UNSUPPORTED;
+    const int hid = a->heads * a->dim_head;
+    CUtensorMap tmX, tmY, tmWqkv, tmWout;
+    const unsigned box[2] = {64u, 128u};
+    {
+        const unsigned long long dims[2] = {static_cast<unsigned long long>(a->C), static_cast<unsigned long long>(a->B) * a->n};
+        const unsigned long long str[2] = {1ull, static_cast<unsigned long long>(a->C)};
+        int r = encode_bf16_map(&tmX, a->x, 2, dims, str, box);
+        if (r != 0) return r;
+        r = encode_bf16_map(&tmY, a->out, 2, dims, str, box);
+        if (r != 0) return r;
+    }
+    {
+        const unsigned long long dims[2] = {static_cast<unsigned long long>(a->C), static_cast<unsigned long long>(3 * hid)};
+        const unsigned long long str[2] = {1ull, static_cast<unsigned long long>(a->C)};
+        const int r = encode_bf16_map(&tmWqkv, a->w_qkv, 2, dims, str, box);
+        if (r != 0) return r;
+    }
+    {
+        const unsigned long long dims[2] = {static_cast<unsigned long long>(hid), static_cast<unsigned long long>(a->C)};
+        const unsigned long long str[2] = {1ull, static_cast<unsigned long long>(hid)};
+        const int r = encode_bf16_map(&tmWout, a->w_out, 2, dims, str, box);
+        if (r != 0) return r;
+    }
+    ddm::launch_linattn_fused(tmX, tmY, tmWqkv, tmWout, a->bias_out, a->g_out, a->mem_kv, a->k_shift, a->B, a->n, a->C, a->n_mem,
+                              g_num_sms, as_stream(stream));
+    return finish(1);
 }
 
 int ddm_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const float* mem_k,

@@ -37,6 +37,10 @@ void launch_stem_tc(const float* in0, int c0, const float* in1, int c1, const fl
 // linattn_tc.cu
 void launch_linattn32_tc(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int n_mem, cudaStream_t s);
 
+// linattn_fused.cu (CUtensorMap-taking launcher declared in api.cu, which includes <cuda.h>)
+int linattn_fused_prepare_attributes();
+bool linattn_fused_supported(int C, int n, int heads, int d, int n_mem);
+
 // attention.cu
 int attention_prepare_attributes();
 int launch_linear_attention(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int d, int n_mem, cudaStream_t s);

@@ -16,9 +16,12 @@ import torch
 
 from . import _lib
 from .arch import AttnSpec, ResBlockSpec, StageSpec, UnetSpec
-from .packing import PackedConv, norm_gain, pack_conv, pack_downsample, pack_linear, pack_stem, pack_upsample
+import os
+
+from .packing import PackedConv, linattn_k_shift, norm_gain, pack_conv, pack_downsample, pack_linear, pack_stem, pack_upsample
 
 MAX_FUSED_NORM = 256     # one CTA owns a full output row in TMEM only up to 256 columns
+MAX_K_SHIFT = 40.0       # fused linear attention: exp(k - shift) must stay a normal fp32 for k >= -shift
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -180,7 +183,7 @@ class UnetEngine:
         skips: List[torch.Tensor] = []
         for st in sp.downs:
             x = self._resblock(st.block1, [x], h, w); skips.append(x)
-            x = self._resblock(st.block2, [x], h, w, want_rnorm=True)
+            x = self._resblock(st.block2, [x], h, w, want_rnorm=not self._linattn_fused(st.attn, h, w))
             x = self._attention(st.attn, x, h, w); skips.append(x)
             x, h, w = self._resample(st, x, h, w)
         if sp.text_mode == "xattn":
@@ -194,7 +197,7 @@ class UnetEngine:
             x = self._cross_attention("cross_attn_up", x, h, w)
         for st in sp.ups:
             x = self._resblock(st.block1, [x, skips.pop()], h, w)
-            x = self._resblock(st.block2, [x, skips.pop()], h, w, want_rnorm=True)
+            x = self._resblock(st.block2, [x, skips.pop()], h, w, want_rnorm=not self._linattn_fused(st.attn, h, w))
             x = self._attention(st.attn, x, h, w)
             x, h, w = self._resample(st, x, h, w)
         x = self._resblock(sp.final_block, [x, h0], h, w)
@@ -299,8 +302,41 @@ class UnetEngine:
         self._last_rnorm = (out, rn)
         return out
 
+    def _linattn_fused(self, at: AttnSpec, h: int, w: int) -> bool:
+        """Whether `attn(x) + x` of this LinearAttention runs as the single fused kernel (ddm_linear_attention_block)."""
+        if at.full or os.environ.get("DDM_NO_FUSED_LINATTN"):
+            return False
+        if not self.lib.ddm_linear_attention_block_supported(at.dim, h * w, at.heads, at.dim_head, at.n_mem):
+            return False
+        shift = linattn_k_shift(self._w[at.name + ".to_qkv.weight"], self._w[at.name + ".norm.g"], self._w[at.name + ".mem_kv"],
+                                at.heads, at.dim_head)
+        return float(shift.max()) <= MAX_K_SHIFT
+
+    def _attention_fused(self, at: AttnSpec, x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+        """LinearAttention block + residual in one launch (dd:173-193, :368)."""
+        B, lib, W_ = self.B, self.lib, self._w
+        wq = self._dev(pack_conv(W_[at.name + ".to_qkv.weight"], in_scale=norm_gain(W_[at.name + ".norm.g"])).weight)
+        wo = self._dev(pack_conv(W_[at.name + ".to_out.0.weight"]).weight)
+        out = self._act(B, h, w, at.dim, at.name)
+        a = _lib.LinAttnBlockArgs()
+        a.x, a.out = x.data_ptr(), out.data_ptr()
+        a.B, a.n, a.C = B, h * w, at.dim
+        a.w_qkv, a.w_out = wq.data_ptr(), wo.data_ptr()
+        a.bias_out = self._f32(at.name + ".to_out.0.bias").data_ptr()
+        a.g_out = self._dev(norm_gain(W_[at.name + ".to_out.1.g"])).data_ptr()
+        a.mem_kv = self._dev(W_[at.name + ".mem_kv"].float()).data_ptr()
+        a.k_shift = self._dev(linattn_k_shift(W_[at.name + ".to_qkv.weight"], W_[at.name + ".norm.g"], W_[at.name + ".mem_kv"],
+                                              at.heads, at.dim_head)).data_ptr()
+        a.heads, a.dim_head, a.n_mem = at.heads, at.dim_head, at.n_mem
+        self._keep.append(a)
+        fn, ref = lib.ddm_linear_attention_block, C.byref(a)
+        self._add(at.name + ".block", lambda s: fn(ref, s))
+        return out
+
     def _attention(self, at: AttnSpec, x: torch.Tensor, h: int, w: int) -> torch.Tensor:
         """`attn(x) + x` with LinearAttention (dd:173-193) or Attention (dd:215-229)."""
+        if self._linattn_fused(at, h, w):
+            return self._attention_fused(at, x, h, w)
         B, lib, W_ = self.B, self.lib, self._w
         n, hid, c = h * w, at.heads * at.dim_head, at.dim
         rows = B * n

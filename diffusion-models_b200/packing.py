@@ -128,3 +128,18 @@ def norm_gain(g: torch.Tensor) -> torch.Tensor:
     """RMSNorm gain with the sqrt(C) factor folded in (denoising_diffusion.py:60-67)."""
     g = g.detach().float().reshape(-1)
     return (g * (g.numel() ** 0.5)).contiguous()
+
+
+def linattn_k_shift(to_qkv_weight: torch.Tensor, norm_g: torch.Tensor, mem_kv: torch.Tensor, heads: int, dim_head: int) -> torch.Tensor:
+    """Per-channel shift for the fused linear attention's softmax over the tokens (denoising_diffusion.py:185).
+
+    k[c][token] = w_c . x_hat with x_hat = x / ||x|| a unit vector (the block's RMSNorm, its gain g * sqrt(C) folded into
+    w_c), so |k| <= ||w_c||_2; the learned memory keys (mem_kv[0], :181) are constants.  softmax is invariant to the
+    shift, so exp(k - bound) / sum replaces the running maximum.  Returns fp32 [heads * dim_head]."""
+    hid = heads * dim_head
+    w = pack_conv(to_qkv_weight, in_scale=norm_gain(norm_g)).weight.float()[hid:2 * hid]      # the bf16 values the kernel multiplies
+    bound = w.norm(dim=1) * 1.01 + 1e-3
+    mem = mem_kv.detach().float()
+    if mem.shape[-1] > 0:
+        bound = torch.maximum(bound, mem[0].reshape(hid, -1).max(dim=1).values.to(bound.device))
+    return bound.contiguous()

@@ -131,6 +131,33 @@ int ddm_linear_attention(const void* qkv_bf16, const float* mem_kv, void* out_bf
                          int n_mem, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * K6f: the whole LinearAttention block as ONE tcgen05 / TMA kernel (dd:173-193 plus the caller's residual dd:368,383):
+ *     out = RMSNorm( W_out . LinAttn( W_qkv . RMSNorm(x) ) + bias_out ) * g_out + x
+ * x, out: bf16 [B, n, C] (out must not alias x).  w_qkv: bf16 [3*heads*dim_head][C] (rows q | k | v, head-major) with
+ * the pre-norm gain g*sqrt(C) folded into its columns; w_out: bf16 [C][heads*dim_head]; g_out = g*sqrt(C) of the
+ * output norm; mem_kv: fp32 [2][heads][dim_head][n_mem]; k_shift: fp32 [heads*dim_head], an upper bound of
+ * k[c][token] per channel (>= ||w_k row c||_2 and >= the channel's memory keys): the softmax over the tokens (dd:185)
+ * is evaluated as exp(k - k_shift[c]) / sum, which is the same value for any shift and cannot overflow for a bound.
+ * Replaces four launches (row norm, to_qkv, ddm_linear_attention, to_out + RMSNorm + residual) and their HBM round
+ * trips.  ddm_linear_attention_block_supported() says whether a shape is covered (C = 64, heads = 4, dim_head = 32,
+ * n a multiple of 128); other shapes use the unfused entry points above.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct ddm_linattn_block_args {
+    const void* x;
+    void* out;
+    int B, n, C;
+    const void* w_qkv;
+    const void* w_out;
+    const float* bias_out;
+    const float* g_out;
+    const float* mem_kv;
+    const float* k_shift;
+    int heads, dim_head, n_mem;
+} ddm_linattn_block_args;
+int ddm_linear_attention_block_supported(int C, int n, int heads, int dim_head, int n_mem);
+int ddm_linear_attention_block(const ddm_linattn_block_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * K7/K8: softmax attention (dd:220-228 + at:109-124; tc:66-77).  q: bf16 rows [B*nq] with row stride ldq, head h at
  * column h*d; k, v likewise over [B*nk] rows; optional learned memory rows mem_k/mem_v fp32 [heads][n_mem][d] are
  * prepended to the keys/values (dd:223-224).  out: bf16 [B*nq][heads*d].  scale = d^-0.5.

@@ -162,6 +162,21 @@ class FakeLib:
         self.view(out, (B, n, heads * d), bf).copy_(y.to(bf))
         return 0
 
+    def ddm_linear_attention_block_supported(self, C_, n, heads, d, n_mem):
+        return 1 if (C_ == 64 and heads == 4 and d == 32 and n >= 128 and n % 128 == 0 and 0 <= n_mem <= 4) else 0
+
+    def ddm_linear_attention_block(self, ref, stream):
+        a = ref._obj
+        self.calls += 1
+        bf, f32 = torch.bfloat16, torch.float32
+        hid = a.heads * a.dim_head
+        x = self.view(a.x, (a.B, a.n, a.C), bf).float()
+        y = R.linattn_block_ref(x, self.view(a.w_qkv, (3 * hid, a.C), bf).float(), self.view(a.w_out, (a.C, hid), bf).float(),
+                                self.view(a.bias_out, (a.C,), f32), self.view(a.g_out, (a.C,), f32),
+                                self.view(a.mem_kv, (2, a.heads, a.dim_head, a.n_mem), f32), a.heads, a.dim_head)
+        self.view(a.out, (a.B, a.n, a.C), bf).copy_(y.to(bf))
+        return 0
+
     def ddm_attention(self, q, ldq, k, ldk, v, ldv, mem_k, mem_v, n_mem, out, B, nq, nk, heads, d, stream):
         self.calls += 1
         bf, f32 = torch.bfloat16, torch.float32

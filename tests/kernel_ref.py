@@ -140,6 +140,24 @@ def linear_attention_ref(qkv, mem_kv, heads, d):
     return bf16_round(out.permute(0, 3, 1, 2).reshape(B, n, heads * d))
 
 
+def linattn_block_ref(x, w_qkv, w_out, bias_out, g_out, mem_kv, heads, d):
+    """ddm_linear_attention_block: x [B,n,C] float (bf16 values); w_qkv [3*heads*d, C] (pre-norm gain folded in),
+    w_out [C, heads*d], g_out = g*sqrt(C); returns bf16-rounded RMSNorm(W_out attn + b) * g + x   (dd:173-193, :368)."""
+    B, n, C = x.shape
+    xn = x / x.pow(2).sum(-1, keepdim=True).sqrt().clamp_min(1e-12)
+    qkv = xn @ w_qkv.t()
+    q, k, v = (z.reshape(B, n, heads, d).permute(0, 2, 3, 1) for z in qkv.chunk(3, dim=-1))   # b h d n
+    k = torch.cat((mem_kv[0][None].expand(B, -1, -1, -1), k), dim=-1)
+    v = torch.cat((mem_kv[1][None].expand(B, -1, -1, -1), v), dim=-1)
+    q = q.softmax(dim=-2) * d ** -0.5
+    k = k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    o = torch.einsum("bhde,bhdn->bhen", ctx, q).permute(0, 3, 1, 2).reshape(B, n, heads * d)
+    y = o @ w_out.t() + bias_out
+    y = y / y.pow(2).sum(-1, keepdim=True).sqrt().clamp_min(1e-12) * g_out
+    return bf16_round(y + x)
+
+
 def attention_ref(q, k, v, mem_k, mem_v, heads, d):
     """q [B,nq,heads*d], k/v [B,nk,heads*d] float; mem_k/mem_v [heads,n_mem,d] or None."""
     B, nq, _ = q.shape

@@ -300,6 +300,40 @@ def test_linear_attention(lib, n, heads, d):
     close(out, R.linear_attention_ref(qkv.float(), mem, heads, d), 2e-2)
 
 
+@pytest.mark.parametrize("B,n,wscale,n_mem", [(3, 1024, 1.0, 4), (2, 128, 1.0, 4), (5, 256, 3.0, 4), (300, 256, 1.0, 4), (2, 4096, 1.0, 4),
+                                              (1, 16384, 0.5, 2), (3, 384, 1.0, 0)])
+def test_linear_attention_block_fused(lib, B, n, wscale, n_mem):
+    """ddm_linear_attention_block (one tcgen05 kernel) against the unfused fp32 statement of dd:173-193 + residual."""
+    from diffusion_models_b200._lib import LinAttnBlockArgs
+    from diffusion_models_b200.packing import linattn_k_shift, norm_gain, pack_conv
+    C_, heads, d = 64, 4, 32
+    hid = heads * d
+    assert lib.ddm_linear_attention_block_supported(C_, n, heads, d, n_mem) == 1
+    x = dev(rnd((B, n, C_), 200) * (1 + rnd((B, n, 1), 201).abs()), BF)      # rows of different lengths
+    w_qkv = rnd((3 * hid, C_, 1, 1), 202, 0.125 * wscale)
+    g_in = rnd((1, C_, 1, 1), 203) * 0.1 + 1
+    w_out = rnd((C_, hid, 1, 1), 204, 0.09)
+    b_out = dev(rnd((C_,), 205, 0.1))
+    g_out = dev(norm_gain(rnd((1, C_, 1, 1), 206) * 0.1 + 1))
+    mem = rnd((2, heads, d, max(n_mem, 1)), 207)[..., :n_mem].contiguous()
+    pq, po = dev(pack_conv(w_qkv, in_scale=norm_gain(g_in)).weight), dev(pack_conv(w_out).weight)
+    shift = dev(linattn_k_shift(w_qkv, g_in, mem, heads, d))
+    memd = dev(mem) if n_mem else None
+    out = torch.zeros((B, n, C_), dtype=BF, device="cuda")
+    a = LinAttnBlockArgs()
+    a.x, a.out, a.B, a.n, a.C = x.data_ptr(), out.data_ptr(), B, n, C_
+    a.w_qkv, a.w_out, a.bias_out, a.g_out = pq.data_ptr(), po.data_ptr(), b_out.data_ptr(), g_out.data_ptr()
+    a.mem_kv, a.k_shift = (memd.data_ptr() if n_mem else None), shift.data_ptr()
+    a.heads, a.dim_head, a.n_mem = heads, d, n_mem
+    check(lib.ddm_linear_attention_block(C.byref(a), stream()))
+    ref = R.linattn_block_ref(x.float(), pq.float(), po.float(), b_out, g_out, dev(mem), heads, d)
+    close(out, ref, 2e-2)
+    out2 = torch.zeros_like(out)                   # bitwise repeatable, and a second launch on the same buffers is clean
+    a.out = out2.data_ptr()
+    check(lib.ddm_linear_attention_block(C.byref(a), stream()))
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("nq,nk,heads,d,n_mem", [(16, 16, 4, 32, 4), (64, 64, 4, 32, 4), (256, 256, 4, 32, 4), (64, 77, 4, 32, 0),
                                                  (16, 1, 4, 32, 0), (16, 16, 2, 16, 4)])
 def test_softmax_attention(lib, nq, nk, heads, d, n_mem):
