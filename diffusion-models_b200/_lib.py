@@ -80,6 +80,9 @@ EXPORTS = {
                                    C.c_void_p, C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_void_p]),
     "ddm_sampler_step_learned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_ulonglong, C.c_longlong, C.c_longlong, C.c_void_p]),
+    "ddm_sampler_step_guided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_ulonglong, C.c_longlong, C.c_void_p]),
     "ddm_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "ddm_select_row": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ddm_randn": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_longlong, C.c_void_p]),

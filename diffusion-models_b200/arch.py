@@ -97,6 +97,11 @@ def build_spec(dim, init_dim=None, out_dim=None, dim_mults=(1, 2, 4, 8), channel
     dims = [init_dim] + [dim * m for m in dim_mults]
     in_out = list(zip(dims[:-1], dims[1:]))
     time_dim = dim * 4
+    # the conv kernel reads channels in 16-byte units and tiles C_out up to 1024 (csrc/conv_tc.cuh kMaxNPad): say so at
+    # construction instead of failing inside the first engine run
+    bad = [c for c in dims if c % 8 != 0 or c > 1024]
+    if bad:
+        raise ValueError(f"Unet widths {dims}: every stage width must be a multiple of 8 and at most 1024 on the B200 path")
     if not full_attn:                                        # dd:289-290 full attention only in the innermost stage
         full_attn = (False,) * (n - 1) + (True,)
     full_attn, heads, dim_head = _tuple(full_attn, n), _tuple(attn_heads, n), _tuple(attn_dim_head, n)

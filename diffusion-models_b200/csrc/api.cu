@@ -75,9 +75,22 @@ const char* ddm_error_string(int code) {
     }
 }
 
+static int init_on_current_device(int device);
+
 int ddm_init(int device) {
-    cudaError_t e = cudaSetDevice(device);
+    // the attribute calls below act on the current device: switch to `device` for their duration only
+    int prev = -1;
+    cudaError_t e = cudaGetDevice(&prev);
     if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int r = init_on_current_device(device);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return r;
+}
+
+static int init_on_current_device(int device) {
+    cudaError_t e;
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -130,7 +143,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.bw_shift = ilog2(p.bw); p.bh_shift = ilog2(p.bh);
     p.tx_shift = ilog2(p.tiles_x); p.ty_shift = ilog2(p.tiles_y);
     p.tiles_pow2 = ((1 << p.tx_shift) == p.tiles_x && (1 << p.ty_shift) == p.tiles_y) ? 1 : 0;
-    if (a->N_pad > 512) return DDM_E_UNSUPPORTED;
+    if (a->N_pad > ddm::kMaxNPad) return DDM_E_UNSUPPORTED;
     p.n_tiles = (a->N_pad + 255) / 256;
     p.block_n = ((a->N_pad + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;   // e.g. N=384 -> 2 tiles of 192
     // C_out = 384 (to_qkv) with one 64-channel K chunk and no fused norm: three tiles of 128 instead of two of 192, so that
@@ -463,7 +476,8 @@ int ddm_linear_attention_block(const ddm_linattn_block_args* a, void* stream) {
     {
         const unsigned long long dims[2] = {static_cast<unsigned long long>(hid), static_cast<unsigned long long>(a->C)};
         const unsigned long long str[2] = {1ull, static_cast<unsigned long long>(hid)};
-        const int r = encode_bf16_map(&tmWout, a->w_out, 2, dims, str, box);
+        const unsigned obox[2] = {64u, static_cast<unsigned>(a->C)};
+        const int r = encode_bf16_map(&tmWout, a->w_out, 2, dims, str, obox);
         if (r != 0) return r;
     }
     ddm::launch_linattn_fused(tmX, tmY, tmWqkv, tmWout, a->bias_out, a->g_out, a->mem_kv, a->k_shift, a->B, a->n, a->C, a->n_mem,
@@ -499,6 +513,19 @@ int ddm_sampler_step_learned(float* x, const float* model_out, const float* nois
     if (numel < 1 || per_sample < 1 || (numel % per_sample) != 0) return DDM_E_BAD_ARGUMENT;
     ddm::launch_sampler_step_learned(x, model_out, noise, noise_step_stride, x_start_out, coef, step_counter, advance, seed, numel,
                                      per_sample, as_stream(stream));
+    return finish(advance ? 2 : 1);
+}
+
+int ddm_sampler_step_guided(float* x, const float* model_out, const float* noise, long long noise_step_stride, const float* guide,
+                            const float* mask, const float* guide_noise, long long guide_noise_step_stride, float* x_start_out,
+                            const float* coef, int* step_counter, int advance, int objective, int clip_denoised, unsigned long long seed,
+                            long long numel, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (x == nullptr || model_out == nullptr || coef == nullptr || step_counter == nullptr || objective < 0 || objective > 2 || numel < 1)
+        return DDM_E_BAD_ARGUMENT;
+    if ((guide == nullptr) != (mask == nullptr)) return DDM_E_BAD_ARGUMENT;
+    ddm::launch_sampler_step_guided(x, model_out, noise, noise_step_stride, guide, mask, guide_noise, guide_noise_step_stride, x_start_out,
+                                    coef, step_counter, advance, objective, clip_denoised, seed, numel, as_stream(stream));
     return finish(advance ? 2 : 1);
 }
 

@@ -26,7 +26,7 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements per k-chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * kChunkK * 2; // 16 KiB
 constexpr int kMaxTaps = 9;
-constexpr int kMaxNPad = 512;
+constexpr int kMaxNPad = 1024;                   // widest C_out (N tiles of at most 256 columns)
 
 struct ConvParams {
     // tile domain (pixel grid the taps are applied on) and tile box

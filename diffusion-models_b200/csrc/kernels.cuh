@@ -24,6 +24,9 @@ void launch_sampler_step(int kind, float* x, const float* mo, const float* noise
                          int advance, int objective, unsigned long long seed, long long numel, cudaStream_t s);
 void launch_sampler_step_learned(float* x, const float* mo, const float* noise, long long noise_stride, float* x0_out, const float* coef,
                                  int* step_counter, int advance, unsigned long long seed, long long numel, long long per_sample, cudaStream_t s);
+void launch_sampler_step_guided(float* x, const float* mo, const float* noise, long long noise_stride, const float* guide, const float* mask,
+                                const float* gnoise, long long gnoise_stride, float* x0_out, const float* coef, int* step_counter, int advance,
+                                int objective, int clip, unsigned long long seed, long long numel, cudaStream_t s);
 void launch_finalize(const float* x, float* y, int unnorm, long long numel, cudaStream_t s);
 void launch_select_row(const float* table, const int* step_counter, float* dst, int row_len, cudaStream_t s);
 void launch_randn(float* x, unsigned long long seed, unsigned long long sid, long long numel, cudaStream_t s);

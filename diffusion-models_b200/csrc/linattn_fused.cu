@@ -6,9 +6,9 @@
 // HBM traffic is one read of x and one write of y (x is read a second time in pass 2, from L2); the 384-channel qkv
 // tensor, the attention output and the to_out result never leave the SM.
 //
-// One CTA per image (persistent over images), 8 warps, no warp specialisation: every warp runs the same program, the
-// elected lane of warp 0 issues TMA loads / stores and MMAs between the CTA barriers; MMAs for the NEXT step are issued
-// before the epilogue of the current one (two accumulator buffers), so the tensor pipe runs under the epilogue math.
+// One CTA per image (persistent over images): 8 epilogue warps + 1 control warp.  The control warp issues every TMA
+// load / store and every MMA and hears from the epilogue warps through mbarriers; MMAs for the NEXT step are issued
+// before the epilogue of the current one finishes (two accumulator buffers), so the tensor pipe runs under the math.
 //
 //   pass 1 (64-token chunks):  [K^T | V^T] = W_kv . x_chunk^T          M = 128 (h,d)/(h,e) rows, N = 64 tokens  (TMEM)
 //        epilogue: thread = channel row; P = exp2(k * rn[tok] * log2e - shift[c]) and V * rn[tok] as bf16 rows in
@@ -18,7 +18,7 @@
 //        ctx[(h,d)][(h',e)] += P_chunk . V_chunk^T                       M = 128, N = 144, K = 64 tokens
 //        (all head pairs; only the diagonal blocks are used; column 128 multiplies a row of ones = sum of P)
 //   between: ctx + learned memory tokens (dd:181-182), / sum, * d^-0.5  -> block-diagonal bf16 [128][128];
-//        M^T[c][(h,d)] = W_out[c][(h,e)] . ctx[(h,d)][(h,e)]^T  folds to_out into the context (dd:191-192 + conv)
+//        M[(h,d)][c] = ctx[(h,d)][(h,e)] . W_out[c][(h,e)]^T  folds to_out into the context (dd:191-192 + conv)
 //   pass 2 (128-token tiles):  Q = x_tile . W_q^T  (M = 128 tokens, N = 128); epilogue: thread = token, softmax over
 //        the 32 channels of each head (dd:184) -> bf16 rows;  Y = softmax(Q) . M  (N = C);  epilogue: + bias, RMSNorm
 //        over C, * g, + x (residual), written in place over the x tile and TMA-stored.
@@ -37,7 +37,9 @@ constexpr int kTileTok = 128;    // tokens per x tile
 constexpr int kChunkTok = 64;    // tokens per pass-1 chunk
 constexpr int kCtxN = 144;       // context accumulator columns (128 + the ones row padded to a multiple of 16)
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads = kEpiThreads + 32;     // + the control warp
 
 struct LaParams {
     const float* bias_out;   // [C]
@@ -53,6 +55,9 @@ struct alignas(8) LaBars {
     uint64_t pvdone[2];      // pass 1: context MMA finished reading P/V buffer
     uint64_t yfull[2];       // pass 2: Y tile ready
     uint64_t wfull, woutfull, mdone;
+    uint64_t edone[2];       // epilogue -> control: pass 1 P/V chunk written (acc read out); pass 2 softmax(q) tile written
+    uint64_t ydone[2];       // epilogue -> control: y tile written in place over the x tile
+    uint64_t cdone, mtdone;
     uint32_t tmem_base;
 };
 
@@ -69,9 +74,9 @@ struct LaSmem {
     static constexpr int kVBytes = kCtxN * 128;                       // V^T[144 rows][64 tok]
     static constexpr int kUBytes = 2 * kPBytes + 2 * kVBytes;         // 69632
     //   pass 1 : P[0] P[1] V[0] V[1]
-    //   between: ctx (bf16 [2 atoms][128][128 B]) at 0, W_out ([2 atoms][128][128 B]) at 32768
+    //   between: ctx (bf16 [2 atoms][128][128 B]) at 0
     //   pass 2 : Qs[0] at 0, Qs[1] at 32768 ([2 atoms][128 tok][128 B] each)
-    static constexpr int off_mt = off_u + kUBytes;                    // M^T [2 atoms][C rows][128 B]
+    static constexpr int off_mt = off_u + kUBytes;                    // M^T [2 atoms][C rows][128 B]; W_out before the M GEMM
     static constexpr int kMtBytes = 2 * C * 128;
     static constexpr int off_small = off_mt + kMtBytes;
     static constexpr int off_rn = off_small;                          // [kNbuf][128] f32
@@ -80,8 +85,8 @@ struct LaSmem {
     static constexpr int off_g = off_bias + C * 4;                    // [C]
     static constexpr int off_pm = off_g + C * 4;                      // [128][4] exp(mem_k - shift)
     static constexpr int off_mv = off_pm + 128 * 16;                  // [128][4] mem_v
-    static constexpr int off_red = off_mv + 128 * 16;                 // [2][128]
-    static constexpr int off_bars = off_red + 2 * 128 * 4;
+    static constexpr int off_red = off_mv + 128 * 16;                 // [2 tiles][2 halves][128]
+    static constexpr int off_bars = off_red + 2 * 2 * 128 * 4;
     static constexpr int kTotal = off_bars + static_cast<int>(sizeof(LaBars));
     static_assert(kTotal + 1024 <= 227 * 1024, "shared-memory plan does not fit");
     static_assert(kUBytes >= 65536, "union region must hold two Qs buffers");
@@ -142,6 +147,9 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_init(&bars->wfull, 1);
         mbar_init(&bars->woutfull, 1);
         mbar_init(&bars->mdone, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->edone[i], kEpiWarps); mbar_init(&bars->ydone[i], kEpiWarps); }
+        mbar_init(&bars->cdone, kEpiWarps);
+        mbar_init(&bars->mtdone, kEpiWarps);
         fence_barrier_init();
         prefetch_tmap(&tmX);
         prefetch_tmap(&tmY);
@@ -167,405 +175,446 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float mcl = __ldg(p.k_shift + row) * kLog2e;       // pass 1: this thread's channel
+    const float mcl = __ldg(p.k_shift + (row & 127)) * kLog2e;       // pass 1: this thread's channel
 
-    if (tid == 0) {     // W_qkv (pre-norm gain folded in) stays resident
-        mbar_arrive_expect_tx(&bars->wfull, static_cast<uint32_t>(L::kWBytes));
-        for (int a = 0; a < kAtoms; ++a)
-            for (int rb = 0; rb < 3; ++rb)
-                tma_load_2d(smem + L::off_w + a * (384 * 128) + rb * (128 * 128), &tmWqkv, &bars->wfull, a * 64, rb * 128);
-    }
-
-    // ---- x-tile stream (thread 0 only): global tile index G = image_iter * 2T + pass * T + t, buffer G % NB
-    int next_load = 0, released = 0;
-    bool store_pending = false;
-    int stored_g = 0;
-    auto pump = [&]() {
-        while (next_load < total_tiles && next_load < released + NB) {
-            const int g = next_load++;
-            const int it = g / (2 * T);
-            const int s = g - it * 2 * T;
-            const int t = s >= T ? s - T : s;
-            const int b = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-            const int slot = g % NB;
-            mbar_arrive_expect_tx(&bars->xfull[slot], static_cast<uint32_t>(L::kXTile));
-            for (int a = 0; a < kAtoms; ++a)
-                tma_load_2d(smem + L::off_x + slot * L::kXTile + a * (kTileTok * 128), &tmX, &bars->xfull[slot], a * 64,
-                            b * p.n + t * kTileTok);
-        }
-    };
     auto wait_leader = [&](uint64_t* bar, uint32_t parity) {    // one polling lane per warp
         if (lane == 0) mbar_wait(bar, parity);
         __syncwarp();
     };
-    auto wait_x = [&](int g) { wait_leader(&bars->xfull[g % NB], static_cast<uint32_t>(g / NB) & 1u); };
-    // per-token 1 / max(||x||, 1e-12) of tile g (the block's pre-norm, dd:176; gain is folded into W_qkv)
-    auto rn_compute = [&](int g) {
-        if (tid < kTileTok) {
-            const int slot = g % NB;
-            float ss = 0.0f;
-#pragma unroll
-            for (int a = 0; a < kAtoms; ++a) {
-                const uint32_t base = sb + L::off_x + slot * L::kXTile + a * (kTileTok * 128) + tid * 128;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint4 v = lds_128u(base + u * 16);
-                    ss = fmaf(bf16_lo(v.x), bf16_lo(v.x), ss); ss = fmaf(bf16_hi(v.x), bf16_hi(v.x), ss);
-                    ss = fmaf(bf16_lo(v.y), bf16_lo(v.y), ss); ss = fmaf(bf16_hi(v.y), bf16_hi(v.y), ss);
-                    ss = fmaf(bf16_lo(v.z), bf16_lo(v.z), ss); ss = fmaf(bf16_hi(v.z), bf16_hi(v.z), ss);
-                    ss = fmaf(bf16_lo(v.w), bf16_lo(v.w), ss); ss = fmaf(bf16_hi(v.w), bf16_hi(v.w), ss);
-                }
-            }
-            const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-            rn_s[slot * 128 + tid] = rn;
-            rnl_s[slot * 128 + tid] = rn * kLog2e;
-        }
-    };
-
     const uint64_t desc0 = umma_desc_sw128(0);
-    const uint32_t idesc_kv = umma_idesc_bf16(128, kChunkTok);
-    const uint32_t idesc_ctx = umma_idesc_bf16(128, kCtxN);
-    const uint32_t idesc_128 = umma_idesc_bf16(128, 128);
-    const uint32_t idesc_y = umma_idesc_bf16(128, C);
     auto desc = [&](uint32_t addr) -> uint64_t { return desc0 | static_cast<uint64_t>((addr & 0x3FFFF) >> 4); };
 
-    // MMA issue helpers (call from warp 0, all lanes; one elected lane issues)
-    auto issue_kv = [&](int g_tile, int j) {          // chunk j of the image -> accumulator buffer j & 1
-        if (elect_one()) {
-            const uint32_t xb = sb + L::off_x + (g_tile % NB) * L::kXTile + (j & 1) * (kChunkTok * 128);
-            const uint32_t d0 = tmem_base + static_cast<uint32_t>((j & 1) * 128);
+    if (warp == kEpiWarps) {
+        // =============================================================================================== control warp
+        // Issues every TMA load / store and every MMA; never touches data.  It learns that the epilogue warps finished
+        // a step through the *done mbarriers (one arrival per epilogue warp) and tells them through the TMA / commit
+        // mbarriers, so the epilogue warps never wait for this warp's instruction issue, only for real completions.
+        const uint32_t idesc_kv = umma_idesc_bf16(128, kChunkTok);
+        const uint32_t idesc_ctx = umma_idesc_bf16(128, kCtxN);
+        const uint32_t idesc_128 = umma_idesc_bf16(128, 128);
+        const uint32_t idesc_y = umma_idesc_bf16(128, C);
+        // x-tile stream: global tile index g = image_iter * 2T + pass * T + t lives in buffer g % NB
+        int next_load = 0, released = 0;
+        auto pump = [&]() {
+            while (next_load < total_tiles && next_load < released + NB) {
+                const int g = next_load++;
+                if (elect_one()) {
+                    const int it = g / (2 * T);
+                    const int s = g - it * 2 * T;
+                    const int t = s >= T ? s - T : s;
+                    const int b = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+                    const int slot = g % NB;
+                    mbar_arrive_expect_tx(&bars->xfull[slot], static_cast<uint32_t>(L::kXTile));
+                    for (int a = 0; a < kAtoms; ++a)
+                        tma_load_2d(smem + L::off_x + slot * L::kXTile + a * (kTileTok * 128), &tmX, &bars->xfull[slot], a * 64,
+                                    b * p.n + t * kTileTok);
+                }
+                __syncwarp();
+            }
+        };
+        auto wait_x = [&](int g) { wait_leader(&bars->xfull[g % NB], static_cast<uint32_t>(g / NB) & 1u); };
+        auto issue_kv = [&](int g_tile, int j) {          // chunk j of the image -> accumulator buffer j & 1
+            if (elect_one()) {
+                const uint32_t xb = sb + L::off_x + (g_tile % NB) * L::kXTile + (j & 1) * (kChunkTok * 128);
+                const uint32_t d0 = tmem_base + static_cast<uint32_t>((j & 1) * 128);
 #pragma unroll
-            for (int kind = 0; kind < 2; ++kind) {
+                for (int kind = 0; kind < 2; ++kind) {
+#pragma unroll
+                    for (int a = 0; a < kAtoms; ++a) {
+                        const uint64_t ad = desc(sb + L::off_w + a * (384 * 128) + (1 + kind) * (128 * 128));
+                        const uint64_t bd = desc(xb + a * (kTileTok * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d0 + kind * 64, ad + 2u * k, bd + 2u * k, idesc_kv, (a | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&bars->accfull[j & 1]);
+            }
+            __syncwarp();
+        };
+        auto issue_ctx = [&](int j) {
+            if (elect_one()) {
+                const uint64_t ad = desc(sb + L::off_u + (j & 1) * L::kPBytes);
+                const uint64_t bd = desc(sb + L::off_u + 2 * L::kPBytes + (j & 1) * L::kVBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256u, ad + 2u * k, bd + 2u * k, idesc_ctx, (j | k) ? 1u : 0u);
+                umma_commit(&bars->pvdone[j & 1]);
+            }
+            __syncwarp();
+        };
+        auto issue_q = [&](int g_tile, int t) {
+            if (elect_one()) {
+                const uint32_t xb = sb + L::off_x + (g_tile % NB) * L::kXTile;
 #pragma unroll
                 for (int a = 0; a < kAtoms; ++a) {
-                    const uint64_t ad = desc(sb + L::off_w + a * (384 * 128) + (1 + kind) * (128 * 128));
-                    const uint64_t bd = desc(xb + a * (kTileTok * 128));
+                    const uint64_t ad = desc(xb + a * (kTileTok * 128));
+                    const uint64_t bd = desc(sb + L::off_w + a * (384 * 128));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(d0 + kind * 64, ad + 2u * k, bd + 2u * k, idesc_kv, (a | k) ? 1u : 0u);
+                        umma_bf16(tmem_base + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_128, (a | k) ? 1u : 0u);
                 }
+                umma_commit(&bars->accfull[t & 1]);
             }
-            umma_commit(&bars->accfull[j & 1]);
+            __syncwarp();
+        };
+        auto issue_y = [&](int t) {
+            if (elect_one()) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const uint64_t ad = desc(sb + L::off_u + (t & 1) * 32768 + a * 16384);
+                    const uint64_t bd = desc(sb + L::off_mt + a * (C * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + 256u + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_y, (a | k) ? 1u : 0u);
+                }
+                umma_commit(&bars->yfull[t & 1]);
+            }
+            __syncwarp();
+        };
+        uint32_t ph_e = 0, ph_yd = 0, ph_misc = 0;       // phase bits of the barriers this warp waits on
+        auto wait_edone = [&](int i) { wait_leader(&bars->edone[i], (ph_e >> i) & 1u); ph_e ^= 1u << i; tc_fence_after(); };
+        auto wait_ydone = [&](int i) { wait_leader(&bars->ydone[i], (ph_yd >> i) & 1u); ph_yd ^= 1u << i; tc_fence_after(); };
+
+        // W_out [C][128] is loaded into the M^T region for every image (16 KB from L2, issued as soon as the previous image's
+        // last Y MMA has read M^T): the M GEMM reads it before the epilogue warps overwrite the region with M^T
+        auto load_wout = [&]() {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&bars->woutfull, static_cast<uint32_t>(L::kMtBytes));
+                for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_mt + a * (C * 128), &tmWout, &bars->woutfull, a * 64, 0);
+            }
+            __syncwarp();
+        };
+        if (elect_one()) {     // W_qkv (pre-norm gain folded in) stays resident
+            mbar_arrive_expect_tx(&bars->wfull, static_cast<uint32_t>(L::kWBytes));
+            for (int a = 0; a < kAtoms; ++a)
+                for (int rb = 0; rb < 3; ++rb)
+                    tma_load_2d(smem + L::off_w + a * (384 * 128) + rb * (128 * 128), &tmWqkv, &bars->wfull, a * 64, rb * 128);
         }
         __syncwarp();
-    };
-    auto issue_ctx = [&](int j) {
-        if (elect_one()) {
-            const uint64_t ad = desc(sb + L::off_u + (j & 1) * L::kPBytes);
-            const uint64_t bd = desc(sb + L::off_u + 2 * L::kPBytes + (j & 1) * L::kVBytes);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256u, ad + 2u * k, bd + 2u * k, idesc_ctx, (j | k) ? 1u : 0u);
-            umma_commit(&bars->pvdone[j & 1]);
-        }
-        __syncwarp();
-    };
-    auto issue_q = [&](int g_tile, int t) {
-        if (elect_one()) {
-            const uint32_t xb = sb + L::off_x + (g_tile % NB) * L::kXTile;
-#pragma unroll
-            for (int a = 0; a < kAtoms; ++a) {
-                const uint64_t ad = desc(xb + a * (kTileTok * 128));
-                const uint64_t bd = desc(sb + L::off_w + a * (384 * 128));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_128, (a | k) ? 1u : 0u);
-            }
-            umma_commit(&bars->accfull[t & 1]);
-        }
-        __syncwarp();
-    };
-    auto issue_y = [&](int t) {
-        if (elect_one()) {
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const uint64_t ad = desc(sb + L::off_u + (t & 1) * 32768 + a * 16384);
-                const uint64_t bd = desc(sb + L::off_mt + a * (C * 128));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base + 256u + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_y, (a | k) ? 1u : 0u);
-            }
-            umma_commit(&bars->yfull[t & 1]);
-        }
-        __syncwarp();
-    };
+        load_wout();
+        pump();
+        wait_leader(&bars->wfull, 0u);
 
-    uint32_t ph_acc = 0, ph_pv = 0, ph_y = 0, ph_wout = 0, ph_m = 0;     // phase bits, one per barrier
-    auto wait_acc = [&](int i) { wait_leader(&bars->accfull[i], (ph_acc >> i) & 1u); ph_acc ^= 1u << i; tc_fence_after(); };
-    auto wait_pv = [&](int i) { wait_leader(&bars->pvdone[i], (ph_pv >> i) & 1u); ph_pv ^= 1u << i; };
-    auto wait_y = [&](int i) { wait_leader(&bars->yfull[i], (ph_y >> i) & 1u); ph_y ^= 1u << i; tc_fence_after(); };
-
-    if (warp == 0) { wait_leader(&bars->wfull, 0u); }
-
-    int G = 0;       // global tile index of the current image's first pass-1 tile
-    for (int it = 0; it < n_img; ++it, G += 2 * T) {
-        const int b = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-        // =========================================================================================== pass 1
-        {   // the V^T buffers' extra rows: row 128 = ones (its context column is the sum of P), rows 129..143 = 0
-            const int vb = tid >> 7, r = (tid & 127) >> 3, u = tid & 7;
-            const uint32_t one2 = r == 0 ? 0x3F803F80u : 0u;
-            sts_128u(sb + L::off_u + 2 * L::kPBytes + vb * L::kVBytes + (128 + r) * 128 + u * 16, one2, one2, one2, one2);
-        }
-        if (tid == 0) {
-            if (store_pending) { bulk_wait_group_read<0>(); released = stored_g + 1; store_pending = false; }
-            pump();
-        }
-        wait_x(G);
-        rn_compute(G);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0) { tc_fence_after(); issue_kv(G, 0); }
-        for (int j = 0; j < J; ++j) {
-            if (j + 1 < J) {
-                const int gt = G + ((j + 1) >> 1);
-                if (((j + 1) & 1) == 0) {
-                    wait_x(gt);
-                    rn_compute(gt);
-                    __syncthreads();
+        int G = 0;
+        int stores_in_flight = 0;      // bulk groups committed and not yet waited for
+        for (int it = 0; it < n_img; ++it, G += 2 * T) {
+            const int b = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            // ---- pass 1
+            wait_x(G);
+            tc_fence_after();
+            issue_kv(G, 0);
+            for (int j = 0; j < J; ++j) {
+                if (j + 1 < J) {
+                    const int gt = G + ((j + 1) >> 1);
+                    if (((j + 1) & 1) == 0) wait_x(gt);
+                    issue_kv(gt, j + 1);        // its accumulator was released by epilogue j - 1 (edone waited below)
                 }
-                if (warp == 0) { tc_fence_after(); issue_kv(gt, j + 1); }
-            }
-            wait_acc(j & 1);
-            if ((j & 1) && tid == 0) { released = G + (j >> 1) + 1; pump(); }
-            if (j >= 2) wait_pv(j & 1);
-            {   // epilogue: thread = channel `row`; tokens half*32 .. +31 of the chunk
-                const int slot = (G + (j >> 1)) % NB;
-                const uint32_t accb = t_lane + static_cast<uint32_t>((j & 1) * 128 + half * 32);
-                uint32_t kr[32], vr[32];
-                tmem_ld32(accb, kr);
-                tmem_ld32(accb + 64u, vr);
-                tmem_ld_wait();
-                const uint32_t rl = sb + L::off_rnl + (slot * 128 + (j & 1) * 64 + half * 32) * 4;
-                const uint32_t r1 = sb + L::off_rn + (slot * 128 + (j & 1) * 64 + half * 32) * 4;
-                const uint32_t prow = sb + L::off_u + (j & 1) * L::kPBytes + row * 128;
-                const uint32_t vrow = sb + L::off_u + 2 * L::kPBytes + (j & 1) * L::kVBytes + row * 128;
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    const float4 a0 = lds_f4(rl + g8 * 32), a1 = lds_f4(rl + g8 * 32 + 16);
-                    const float4 b0 = lds_f4(r1 + g8 * 32), b1 = lds_f4(r1 + g8 * 32 + 16);
-                    const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    const float bl[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    uint32_t pw[4], vw[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(kr[g8 * 8 + 2 * i]), al[2 * i], -mcl));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(kr[g8 * 8 + 2 * i + 1]), al[2 * i + 1], -mcl));
-                        pw[i] = pack_bf16x2(p0, p1);
-                        vw[i] = pack_bf16x2(__uint_as_float(vr[g8 * 8 + 2 * i]) * bl[2 * i], __uint_as_float(vr[g8 * 8 + 2 * i + 1]) * bl[2 * i + 1]);
-                    }
-                    const uint32_t uo = static_cast<uint32_t>(((half * 4 + g8) ^ sw) << 4);
-                    sts_128u(prow + uo, pw[0], pw[1], pw[2], pw[3]);
-                    sts_128u(vrow + uo, vw[0], vw[1], vw[2], vw[3]);
+                wait_edone(j & 1);              // P/V of chunk j written, accumulator j & 1 read out
+                issue_ctx(j);
+                if (j & 1) {                    // both chunks of tile j >> 1 multiplied (epilogue j saw accfull) and its norms taken
+                    if (stores_in_flight) { if (elect_one()) bulk_wait_group_read<0>(); __syncwarp(); stores_in_flight = 0; }
+                    released = G + (j >> 1) + 1;
+                    pump();
                 }
             }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();
-            if (warp == 0) { tc_fence_after(); issue_ctx(j); }
-        }
-        wait_pv(J & 1);            // chunk J-2
-        wait_pv((J - 1) & 1);      // chunk J-1: the context is complete
-        tc_fence_after();
-
-        // =========================================================================================== between the passes
-        if (tid == 0) {     // W_out -> union region (the V buffers are dead); rows >= C are zero-filled by TMA
-            mbar_arrive_expect_tx(&bars->woutfull, 32768u);
-            for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_u + 32768 + a * 16384, &tmWout, &bars->woutfull, a * 64, 0);
-        }
-        if (half == 0) {    // head q, channel d = lane: context row, normalised, d^-0.5 folded in (dd:187)
-            uint32_t cr[32];
-            tmem_ld32(t_lane + 256u + static_cast<uint32_t>(q * 32), cr);
-            float ksum = __uint_as_float(tmem_ld1(t_lane + 256u + 128u));
-            tmem_ld_wait();
-            const float4 pm = *reinterpret_cast<const float4*>(pm_s + row * 4);
-            ksum += (pm.x + pm.y) + (pm.z + pm.w);
-            const float sc = 0.17677669529663687f / ksum;     // 32^-0.5 / sum
-            const uint32_t crow = sb + L::off_u + (q >> 1) * 16384 + row * 128;
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-                uint32_t w[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float v[2];
-#pragma unroll
-                    for (int e2 = 0; e2 < 2; ++e2) {
-                        const int e = g8 * 8 + 2 * i + e2;
-                        const float4 mv = *reinterpret_cast<const float4*>(mv_s + (q * 32 + e) * 4);     // warp-uniform address
-                        float c = __uint_as_float(cr[e]);
-                        c = fmaf(pm.x, mv.x, c); c = fmaf(pm.y, mv.y, c); c = fmaf(pm.z, mv.z, c); c = fmaf(pm.w, mv.w, c);
-                        v[e2] = c * sc;
-                    }
-                    w[i] = pack_bf16x2(v[0], v[1]);
-                }
-                sts_128u(crow + static_cast<uint32_t>((((q & 1) * 4 + g8) ^ sw) << 4), w[0], w[1], w[2], w[3]);
-            }
-        } else {            // the other heads' columns of this row are zero (block-diagonal context)
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (!(a == (q >> 1) && (u >> 2) == (q & 1)))
-                        sts_128u(sb + L::off_u + a * 16384 + row * 128 + static_cast<uint32_t>((u ^ sw) << 4), 0u, 0u, 0u, 0u);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0) {
-            wait_leader(&bars->woutfull, ph_wout);
+            // ---- between the passes: M[(h,d)][c] = ctx[(h,d)][(h',e)] . W_out[c][(h',e)]^T   (W_out sits in the M^T region)
+            wait_leader(&bars->cdone, ph_misc & 1u);          // block-diagonal context written (every context MMA retired)
+            wait_leader(&bars->woutfull, ph_misc & 1u);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
-                    const uint64_t ad = desc(sb + L::off_u + 32768 + a * 16384);
-                    const uint64_t bd = desc(sb + L::off_u + a * 16384);
+                    const uint64_t ad = desc(sb + L::off_u + a * 16384);
+                    const uint64_t bd = desc(sb + L::off_mt + a * (C * 128));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc_128, (a | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc_y, (a | k) ? 1u : 0u);
                 }
                 umma_commit(&bars->mdone);
             }
             __syncwarp();
-        }
-        ph_wout ^= 1u;
-        wait_leader(&bars->mdone, ph_m);
-        ph_m ^= 1u;
-        tc_fence_after();
-        if (q * 32 < C) {   // thread = output channel `row` of M^T; columns (h,d) = half*64 .. +63 (one 128-byte atom row)
-            uint32_t m0[32], m1[32];
-            tmem_ld32(t_lane + static_cast<uint32_t>(half * 64), m0);
-            tmem_ld32(t_lane + static_cast<uint32_t>(half * 64 + 32), m1);
-            tmem_ld_wait();
-            const uint32_t mrow = sb + L::off_mt + half * (C * 128) + row * 128;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                sts_128u(mrow + static_cast<uint32_t>((u ^ sw) << 4),
-                         pack_bf16x2(__uint_as_float(m0[8 * u]), __uint_as_float(m0[8 * u + 1])),
-                         pack_bf16x2(__uint_as_float(m0[8 * u + 2]), __uint_as_float(m0[8 * u + 3])),
-                         pack_bf16x2(__uint_as_float(m0[8 * u + 4]), __uint_as_float(m0[8 * u + 5])),
-                         pack_bf16x2(__uint_as_float(m0[8 * u + 6]), __uint_as_float(m0[8 * u + 7])));
-                sts_128u(mrow + static_cast<uint32_t>(((u + 4) ^ sw) << 4),
-                         pack_bf16x2(__uint_as_float(m1[8 * u]), __uint_as_float(m1[8 * u + 1])),
-                         pack_bf16x2(__uint_as_float(m1[8 * u + 2]), __uint_as_float(m1[8 * u + 3])),
-                         pack_bf16x2(__uint_as_float(m1[8 * u + 4]), __uint_as_float(m1[8 * u + 5])),
-                         pack_bf16x2(__uint_as_float(m1[8 * u + 6]), __uint_as_float(m1[8 * u + 7])));
-            }
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-
-        // =========================================================================================== pass 2
-        const int G2 = G + T;
-        auto epilogue_y = [&](int u_t) {
-            wait_y(u_t & 1);
-            const int slot = (G2 + u_t) % NB;
-            constexpr int kCols = C / 2;                      // columns of this thread: half * kCols .. +kCols-1
-            const uint32_t accb = t_lane + 256u + static_cast<uint32_t>((u_t & 1) * 128 + half * kCols);
-            float v[kCols];
-            float ss = 0.0f;
-#pragma unroll
-            for (int c32 = 0; c32 < kCols / 32; ++c32) {
-                uint32_t yr[32];
-                tmem_ld32(accb + c32 * 32, yr);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 bb = lds_f4(sb + L::off_bias + (half * kCols + c32 * 32 + i) * 4);
-                    v[c32 * 32 + i] = __uint_as_float(yr[i]) + bb.x;
-                    v[c32 * 32 + i + 1] = __uint_as_float(yr[i + 1]) + bb.y;
-                    v[c32 * 32 + i + 2] = __uint_as_float(yr[i + 2]) + bb.z;
-                    v[c32 * 32 + i + 3] = __uint_as_float(yr[i + 3]) + bb.w;
-                    ss = fmaf(v[c32 * 32 + i], v[c32 * 32 + i], ss);
-                    ss = fmaf(v[c32 * 32 + i + 1], v[c32 * 32 + i + 1], ss);
-                    ss = fmaf(v[c32 * 32 + i + 2], v[c32 * 32 + i + 2], ss);
-                    ss = fmaf(v[c32 * 32 + i + 3], v[c32 * 32 + i + 3], ss);
+            wait_leader(&bars->mtdone, ph_misc & 1u);         // M^T written, its accumulator read out
+            ph_misc ^= 1u;
+            tc_fence_after();
+            // ---- pass 2
+            const int G2 = G + T;
+            wait_x(G2);
+            issue_q(G2, 0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) {
+                    wait_x(G2 + t + 1);
+                    issue_q(G2 + t + 1, t + 1);     // its accumulator was released by epilogue Q t - 1
+                }
+                wait_edone(t & 1);                  // softmax(q) tile written
+                issue_y(t);                         // its accumulator was released by epilogue Y t - 2 (ydone waited below)
+                if (t >= 1) {
+                    wait_ydone((t - 1) & 1);
+                    if (elect_one()) {
+                        // the previous store has read its tile by now: hand that buffer back to the loader first
+                        if (stores_in_flight) bulk_wait_group_read<0>();
+                        for (int a = 0; a < kAtoms; ++a)
+                            tma_store_2d(&tmY, smem + L::off_x + ((G2 + t - 1) % NB) * L::kXTile + a * (kTileTok * 128), a * 64,
+                                         b * p.n + (t - 1) * kTileTok);
+                        bulk_commit_group();
+                    }
+                    __syncwarp();
+                    if (stores_in_flight) { released = G2 + t - 1; pump(); }
+                    stores_in_flight = 1;
                 }
             }
-            red_s[half * 128 + row] = ss;
-            tc_fence_before();
-            __syncthreads();
-            const float rinv = 1.0f / fmaxf(sqrtf(red_s[row] + red_s[128 + row]), 1e-12f);
-            // residual x (own row of the tile), result written in place; column c lives in atom c / 64, unit (c % 64) / 8
-            const uint32_t xrow = sb + L::off_x + slot * L::kXTile + row * 128;
-#pragma unroll
-            for (int u8 = 0; u8 < kCols / 8; ++u8) {
-                const int c0 = half * kCols + u8 * 8;
-                const uint32_t addr = xrow + (c0 >> 6) * (kTileTok * 128) + static_cast<uint32_t>(((((c0 & 63) >> 3)) ^ sw) << 4);
-                const uint4 xr = lds_128u(addr);
-                const float4 g0 = lds_f4(sb + L::off_g + c0 * 4), g1 = lds_f4(sb + L::off_g + c0 * 4 + 16);
-                const float* vv = v + u8 * 8;
-                const uint32_t w0 = pack_bf16x2(fmaf(vv[0] * rinv, g0.x, bf16_lo(xr.x)), fmaf(vv[1] * rinv, g0.y, bf16_hi(xr.x)));
-                const uint32_t w1 = pack_bf16x2(fmaf(vv[2] * rinv, g0.z, bf16_lo(xr.y)), fmaf(vv[3] * rinv, g0.w, bf16_hi(xr.y)));
-                const uint32_t w2 = pack_bf16x2(fmaf(vv[4] * rinv, g1.x, bf16_lo(xr.z)), fmaf(vv[5] * rinv, g1.y, bf16_hi(xr.z)));
-                const uint32_t w3 = pack_bf16x2(fmaf(vv[6] * rinv, g1.z, bf16_lo(xr.w)), fmaf(vv[7] * rinv, g1.w, bf16_hi(xr.w)));
-                sts_128u(addr, w0, w1, w2, w3);
-            }
-            fence_proxy_async();
-            __syncthreads();
-            if (tid == 0) {
+            wait_ydone((T - 1) & 1);
+            if (elect_one()) {
+                if (stores_in_flight) bulk_wait_group_read<0>();
                 for (int a = 0; a < kAtoms; ++a)
-                    tma_store_2d(&tmY, smem + L::off_x + slot * L::kXTile + a * (kTileTok * 128), a * 64, b * p.n + u_t * kTileTok);
+                    tma_store_2d(&tmY, smem + L::off_x + ((G2 + T - 1) % NB) * L::kXTile + a * (kTileTok * 128), a * 64,
+                                 b * p.n + (T - 1) * kTileTok);
                 bulk_commit_group();
-                store_pending = true;
-                stored_g = G2 + u_t;
+            }
+            __syncwarp();
+            if (stores_in_flight) { released = G2 + T - 1; pump(); }
+            stores_in_flight = 1;
+            if (it + 1 < n_img) load_wout();
+        }
+        if (elect_one()) bulk_wait_group<0>();
+        __syncwarp();
+    } else {
+        // =============================================================================================== epilogue warps
+        auto wait_x = [&](int g) { wait_leader(&bars->xfull[g % NB], static_cast<uint32_t>(g / NB) & 1u); };
+        auto arrive = [&](uint64_t* bar) {     // this warp's generic-proxy writes / TMEM reads are done
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        };
+        // per-token 1 / max(||x||, 1e-12) of tile g (the block's pre-norm, dd:176; gain is folded into W_qkv)
+        auto rn_compute = [&](int g) {
+            if (tid < kTileTok) {
+                const int slot = g % NB;
+                float ss = 0.0f;
+#pragma unroll
+                for (int a = 0; a < kAtoms; ++a) {
+                    const uint32_t base = sb + L::off_x + slot * L::kXTile + a * (kTileTok * 128) + tid * 128;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint4 v = lds_128u(base + static_cast<uint32_t>((u ^ (tid & 7)) << 4));      // any order: it is a sum
+                        ss = fmaf(bf16_lo(v.x), bf16_lo(v.x), ss); ss = fmaf(bf16_hi(v.x), bf16_hi(v.x), ss);
+                        ss = fmaf(bf16_lo(v.y), bf16_lo(v.y), ss); ss = fmaf(bf16_hi(v.y), bf16_hi(v.y), ss);
+                        ss = fmaf(bf16_lo(v.z), bf16_lo(v.z), ss); ss = fmaf(bf16_hi(v.z), bf16_hi(v.z), ss);
+                        ss = fmaf(bf16_lo(v.w), bf16_lo(v.w), ss); ss = fmaf(bf16_hi(v.w), bf16_hi(v.w), ss);
+                    }
+                }
+                const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                rn_s[slot * 128 + tid] = rn;
+                rnl_s[slot * 128 + tid] = rn * kLog2e;
             }
         };
+        uint32_t ph_acc = 0, ph_pv = 0, ph_y = 0, ph_m = 0;     // phase bits, one per barrier
+        auto wait_acc = [&](int i) { wait_leader(&bars->accfull[i], (ph_acc >> i) & 1u); ph_acc ^= 1u << i; tc_fence_after(); };
+        auto wait_pv = [&](int i) { wait_leader(&bars->pvdone[i], (ph_pv >> i) & 1u); ph_pv ^= 1u << i; };
+        auto wait_y = [&](int i) { wait_leader(&bars->yfull[i], (ph_y >> i) & 1u); ph_y ^= 1u << i; tc_fence_after(); };
 
-        wait_x(G2);
-        rn_compute(G2);
-        __syncthreads();
-        if (warp == 0) { tc_fence_after(); issue_q(G2, 0); }
-        for (int t = 0; t < T; ++t) {
-            if (t + 1 < T) {
-                if (tid == 0) {
-                    if (store_pending) { bulk_wait_group_read<0>(); released = stored_g + 1; store_pending = false; }
-                    pump();
-                }
-                wait_x(G2 + t + 1);
-                rn_compute(G2 + t + 1);
-                __syncthreads();
-                if (warp == 0) { tc_fence_after(); issue_q(G2 + t + 1, t + 1); }
+        int G = 0;       // global tile index of the current image's first pass-1 tile
+        for (int it = 0; it < n_img; ++it, G += 2 * T) {
+            // ======================================================================================= pass 1
+            {   // the V^T buffers' extra rows: row 128 = ones (its context column is the sum of P), rows 129..143 = 0
+                const int vb = tid >> 7, r = (tid & 127) >> 3, u = tid & 7;
+                const uint32_t one2 = r == 0 ? 0x3F803F80u : 0u;
+                sts_128u(sb + L::off_u + 2 * L::kPBytes + vb * L::kVBytes + (128 + r) * 128 + u * 16, one2, one2, one2, one2);
+                // published to the context MMA by the fence + arrival that follows chunk 0 (edone)
             }
-            wait_acc(t & 1);
-            {   // epilogue: thread = token `row`; heads 2*half, 2*half+1 -> softmax over the 32 channels of each (dd:184)
-                const int slot = (G2 + t) % NB;
-                const float rnl = rnl_s[slot * 128 + row];
-                const uint32_t accb = t_lane + static_cast<uint32_t>((t & 1) * 128 + half * 64);
-                const uint32_t qrow = sb + L::off_u + (t & 1) * 32768 + half * 16384 + row * 128;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t qr[32];
-                    tmem_ld32(accb + hh * 32, qr);
+            for (int j = 0; j < J; ++j) {
+                const int gt = G + (j >> 1);
+                if ((j & 1) == 0) {
+                    wait_x(gt);
+                    rn_compute(gt);
+                    named_bar_sync(1, kEpiThreads);
+                }
+                wait_acc(j & 1);
+                if (j >= 2) wait_pv(j & 1);
+                {   // epilogue: thread = channel `row`; tokens half*32 .. +31 of the chunk
+                    const int slot = gt % NB;
+                    const uint32_t accb = t_lane + static_cast<uint32_t>((j & 1) * 128 + half * 32);
+                    uint32_t kr[32], vr[32];
+                    tmem_ld32(accb, kr);
+                    tmem_ld32(accb + 64u, vr);
                     tmem_ld_wait();
-                    float m = __uint_as_float(qr[0]);
+                    const uint32_t rl = sb + L::off_rnl + (slot * 128 + (j & 1) * 64 + half * 32) * 4;
+                    const uint32_t r1 = sb + L::off_rn + (slot * 128 + (j & 1) * 64 + half * 32) * 4;
+                    const uint32_t prow = sb + L::off_u + (j & 1) * L::kPBytes + row * 128;
+                    const uint32_t vrow = sb + L::off_u + 2 * L::kPBytes + (j & 1) * L::kVBytes + row * 128;
 #pragma unroll
-                    for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(qr[i]));
-                    const float mm = m * rnl;
-                    float e[32];
-                    float s0 = 0.0f, s1 = 0.0f;
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const float4 a0 = lds_f4(rl + g8 * 32), a1 = lds_f4(rl + g8 * 32 + 16);
+                        const float4 b0 = lds_f4(r1 + g8 * 32), b1 = lds_f4(r1 + g8 * 32 + 16);
+                        const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        const float bl[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        uint32_t pw[4], vw[4];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        e[i] = ex2_approx(fmaf(__uint_as_float(qr[i]), rnl, -mm));
-                        e[i + 1] = ex2_approx(fmaf(__uint_as_float(qr[i + 1]), rnl, -mm));
-                        s0 += e[i];
-                        s1 += e[i + 1];
+                        for (int i = 0; i < 4; ++i) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(kr[g8 * 8 + 2 * i]), al[2 * i], -mcl));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(kr[g8 * 8 + 2 * i + 1]), al[2 * i + 1], -mcl));
+                            pw[i] = pack_bf16x2(p0, p1);
+                            vw[i] = pack_bf16x2(__uint_as_float(vr[g8 * 8 + 2 * i]) * bl[2 * i], __uint_as_float(vr[g8 * 8 + 2 * i + 1]) * bl[2 * i + 1]);
+                        }
+                        const uint32_t uo = static_cast<uint32_t>(((half * 4 + g8) ^ sw) << 4);
+                        sts_128u(prow + uo, pw[0], pw[1], pw[2], pw[3]);
+                        sts_128u(vrow + uo, vw[0], vw[1], vw[2], vw[3]);
                     }
-                    const float inv = 1.0f / (s0 + s1);
+                }
+                arrive(&bars->edone[j & 1]);
+            }
+            wait_pv(J & 1);            // chunk J-2
+            wait_pv((J - 1) & 1);      // chunk J-1: the context is complete
+            tc_fence_after();
+
+            // ======================================================================================= between the passes
+            if (half == 0) {    // head q, channel d = lane: context row, normalised, d^-0.5 folded in (dd:187)
+                uint32_t cr[32];
+                tmem_ld32(t_lane + 256u + static_cast<uint32_t>(q * 32), cr);
+                float ksum = __uint_as_float(tmem_ld1(t_lane + 256u + 128u));
+                tmem_ld_wait();
+                const float4 pm = *reinterpret_cast<const float4*>(pm_s + row * 4);
+                ksum += (pm.x + pm.y) + (pm.z + pm.w);
+                const float sc = 0.17677669529663687f / ksum;     // 32^-0.5 / sum
+                const uint32_t crow = sb + L::off_u + (q >> 1) * 16384 + row * 128;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        sts_128u(qrow + static_cast<uint32_t>(((hh * 4 + u) ^ sw) << 4),
-                                 pack_bf16x2(e[8 * u] * inv, e[8 * u + 1] * inv), pack_bf16x2(e[8 * u + 2] * inv, e[8 * u + 3] * inv),
-                                 pack_bf16x2(e[8 * u + 4] * inv, e[8 * u + 5] * inv), pack_bf16x2(e[8 * u + 6] * inv, e[8 * u + 7] * inv));
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float v[2];
+#pragma unroll
+                        for (int e2 = 0; e2 < 2; ++e2) {
+                            const int e = g8 * 8 + 2 * i + e2;
+                            const float4 mv = *reinterpret_cast<const float4*>(mv_s + (q * 32 + e) * 4);     // warp-uniform address
+                            float c = __uint_as_float(cr[e]);
+                            c = fmaf(pm.x, mv.x, c); c = fmaf(pm.y, mv.y, c); c = fmaf(pm.z, mv.z, c); c = fmaf(pm.w, mv.w, c);
+                            v[e2] = c * sc;
+                        }
+                        w[i] = pack_bf16x2(v[0], v[1]);
+                    }
+                    sts_128u(crow + static_cast<uint32_t>((((q & 1) * 4 + g8) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+                }
+            } else {            // the other heads' columns of this row are zero (block-diagonal context)
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (!(a == (q >> 1) && (u >> 2) == (q & 1)))
+                            sts_128u(sb + L::off_u + a * 16384 + row * 128 + static_cast<uint32_t>((u ^ sw) << 4), 0u, 0u, 0u, 0u);
+            }
+            arrive(&bars->cdone);
+            wait_leader(&bars->mdone, ph_m);
+            ph_m ^= 1u;
+            tc_fence_after();
+            {   // thread = row (h,d) of M; columns c = half * C/2 .. ; stored transposed as M^T[c][(h,d)] (K-major B operand of Y)
+                constexpr int kMc = C / 2;
+                const uint32_t mbase = sb + L::off_mt + (row >> 6) * (C * 128) + static_cast<uint32_t>((row & 7) * 2);
+                const int ku = (row & 63) >> 3;
+#pragma unroll
+                for (int c32 = 0; c32 < kMc / 32; ++c32) {
+                    uint32_t mr[32];
+                    tmem_ld32(t_lane + static_cast<uint32_t>(half * kMc + c32 * 32), mr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int c = half * kMc + c32 * 32 + i;
+                        const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(mr[i])));
+                        asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(mbase + c * 128 + static_cast<uint32_t>((ku ^ (c & 7)) << 4)), "h"(hv) : "memory");
+                    }
                 }
             }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();
-            if (warp == 0) { tc_fence_after(); issue_y(t); }
-            if (t >= 1) epilogue_y(t - 1);
+            arrive(&bars->mtdone);
+
+            // ======================================================================================= pass 2
+            const int G2 = G + T;
+            auto epilogue_y = [&](int u_t) {
+                wait_y(u_t & 1);
+                const int slot = (G2 + u_t) % NB;
+                constexpr int kCols = C / 2;                      // columns of this thread: half * kCols .. +kCols-1
+                const uint32_t accb = t_lane + 256u + static_cast<uint32_t>((u_t & 1) * 128 + half * kCols);
+                float v[kCols];
+                float ss = 0.0f;
+#pragma unroll
+                for (int c32 = 0; c32 < kCols / 32; ++c32) {
+                    uint32_t yr[32];
+                    tmem_ld32(accb + c32 * 32, yr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bb = lds_f4(sb + L::off_bias + (half * kCols + c32 * 32 + i) * 4);
+                        v[c32 * 32 + i] = __uint_as_float(yr[i]) + bb.x;
+                        v[c32 * 32 + i + 1] = __uint_as_float(yr[i + 1]) + bb.y;
+                        v[c32 * 32 + i + 2] = __uint_as_float(yr[i + 2]) + bb.z;
+                        v[c32 * 32 + i + 3] = __uint_as_float(yr[i + 3]) + bb.w;
+                        ss = fmaf(v[c32 * 32 + i], v[c32 * 32 + i], ss);
+                        ss = fmaf(v[c32 * 32 + i + 1], v[c32 * 32 + i + 1], ss);
+                        ss = fmaf(v[c32 * 32 + i + 2], v[c32 * 32 + i + 2], ss);
+                        ss = fmaf(v[c32 * 32 + i + 3], v[c32 * 32 + i + 3], ss);
+                    }
+                }
+                red_s[(u_t & 1) * 256 + half * 128 + row] = ss;
+                named_bar_sync(1, kEpiThreads);
+                const float rinv = 1.0f / fmaxf(sqrtf(red_s[(u_t & 1) * 256 + row] + red_s[(u_t & 1) * 256 + 128 + row]), 1e-12f);
+                // residual x (own row of the tile), result written in place; column c lives in atom c / 64, unit (c % 64) / 8
+                const uint32_t xrow = sb + L::off_x + slot * L::kXTile + row * 128;
+#pragma unroll
+                for (int u8 = 0; u8 < kCols / 8; ++u8) {
+                    const int c0 = half * kCols + u8 * 8;
+                    const uint32_t addr = xrow + (c0 >> 6) * (kTileTok * 128) + static_cast<uint32_t>(((((c0 & 63) >> 3)) ^ sw) << 4);
+                    const uint4 xr = lds_128u(addr);
+                    const float4 g0 = lds_f4(sb + L::off_g + c0 * 4), g1 = lds_f4(sb + L::off_g + c0 * 4 + 16);
+                    const float* vv = v + u8 * 8;
+                    const uint32_t w0 = pack_bf16x2(fmaf(vv[0] * rinv, g0.x, bf16_lo(xr.x)), fmaf(vv[1] * rinv, g0.y, bf16_hi(xr.x)));
+                    const uint32_t w1 = pack_bf16x2(fmaf(vv[2] * rinv, g0.z, bf16_lo(xr.y)), fmaf(vv[3] * rinv, g0.w, bf16_hi(xr.y)));
+                    const uint32_t w2 = pack_bf16x2(fmaf(vv[4] * rinv, g1.x, bf16_lo(xr.z)), fmaf(vv[5] * rinv, g1.y, bf16_hi(xr.z)));
+                    const uint32_t w3 = pack_bf16x2(fmaf(vv[6] * rinv, g1.z, bf16_lo(xr.w)), fmaf(vv[7] * rinv, g1.w, bf16_hi(xr.w)));
+                    sts_128u(addr, w0, w1, w2, w3);
+                }
+                arrive(&bars->ydone[u_t & 1]);
+            };
+
+            for (int t = 0; t < T; ++t) {
+                wait_x(G2 + t);
+                rn_compute(G2 + t);
+                named_bar_sync(1, kEpiThreads);
+                wait_acc(t & 1);
+                {   // epilogue: thread = token `row`; heads 2*half, 2*half+1 -> softmax over the 32 channels of each (dd:184)
+                    const int slot = (G2 + t) % NB;
+                    const float rnl = rnl_s[slot * 128 + row];
+                    const uint32_t accb = t_lane + static_cast<uint32_t>((t & 1) * 128 + half * 64);
+                    const uint32_t qrow = sb + L::off_u + (t & 1) * 32768 + half * 16384 + row * 128;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t qr[32];
+                        tmem_ld32(accb + hh * 32, qr);
+                        tmem_ld_wait();
+                        float m = __uint_as_float(qr[0]);
+#pragma unroll
+                        for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(qr[i]));
+                        const float mm = m * rnl;
+                        float e[32];
+                        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            e[i] = ex2_approx(fmaf(__uint_as_float(qr[i]), rnl, -mm));
+                            e[i + 1] = ex2_approx(fmaf(__uint_as_float(qr[i + 1]), rnl, -mm));
+                            s0 += e[i];
+                            s1 += e[i + 1];
+                        }
+                        const float inv = 1.0f / (s0 + s1);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            sts_128u(qrow + static_cast<uint32_t>(((hh * 4 + u) ^ sw) << 4),
+                                     pack_bf16x2(e[8 * u] * inv, e[8 * u + 1] * inv), pack_bf16x2(e[8 * u + 2] * inv, e[8 * u + 3] * inv),
+                                     pack_bf16x2(e[8 * u + 4] * inv, e[8 * u + 5] * inv), pack_bf16x2(e[8 * u + 6] * inv, e[8 * u + 7] * inv));
+                    }
+                }
+                arrive(&bars->edone[t & 1]);
+                if (t >= 1) epilogue_y(t - 1);
+            }
+            epilogue_y(T - 1);
         }
-        epilogue_y(T - 1);
     }
-    if (tid == 0) bulk_wait_group<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {

@@ -389,6 +389,59 @@ sampler_step_kernel(int kind, float* __restrict__ x, const float* __restrict__ m
     }
 }
 
+// Guided DDIM step (denoising_diffusion.py:710-777 ddim_sample_guided): model_predictions WITHOUT re-deriving the noise
+// (rederive_pred_noise is left at False there), optional x0 clamp, the DDIM update, then the known region is replaced by
+// the guide noised to step t:  x = x * mask + q_sample(guide, t) * (1 - mask)   (dd:747-749; not on the last step).
+__global__ void __launch_bounds__(256)
+sampler_step_guided_kernel(float* __restrict__ x, const float* __restrict__ mo, const float* __restrict__ noise_base, long long noise_stride,
+                           const float* __restrict__ guide, const float* __restrict__ mask, const float* __restrict__ gnoise_base,
+                           long long gnoise_stride, float* __restrict__ x0_out, const float* __restrict__ coef_tab,
+                           int* __restrict__ step_counter, int objective, int clip, unsigned long long seed, long long numel) {
+    const int step = *step_counter;
+    const float* noise = noise_base != nullptr ? noise_base + static_cast<long long>(step) * noise_stride : nullptr;
+    const float* gnoise = gnoise_base != nullptr ? gnoise_base + static_cast<long long>(step) * gnoise_stride : nullptr;
+    const float* cf = coef_tab + static_cast<long long>(step) * 8;
+    const float ra = cf[0], rm1 = cf[1], k2 = cf[2], k3 = cf[3], sigma = cf[4], last = cf[5], sac = cf[6], s1m = cf[7];
+    const long long grp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i0 = grp * 4;
+    if (i0 >= numel) return;
+    const unsigned long long epoch = static_cast<unsigned long long>(static_cast<unsigned>(step_counter[1])) << 32;
+    float z[4] = {0.f, 0.f, 0.f, 0.f}, zg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sigma != 0.0f && noise == nullptr && last == 0.0f)
+        normal4(seed, epoch | (static_cast<unsigned long long>(step) + 1ull), static_cast<unsigned long long>(grp), z);
+    if (guide != nullptr && gnoise == nullptr && last == 0.0f)
+        normal4(seed, epoch | (0x40000000ull + static_cast<unsigned long long>(step)), static_cast<unsigned long long>(grp), zg);
+    for (int j = 0; j < 4 && i0 + j < numel; ++j) {
+        const long long i = i0 + j;
+        const float xt = x[i], o = mo[i];
+        const float rax = __fmul_rn(ra, xt);
+        float x0, eps;
+        if (objective == 0) {
+            x0 = __fsub_rn(rax, __fmul_rn(rm1, o));
+            if (clip) x0 = clamp1(x0);
+            eps = o;
+        } else {
+            x0 = (objective == 1) ? o : __fsub_rn(__fmul_rn(sac, xt), __fmul_rn(s1m, o));
+            if (clip) x0 = clamp1(x0);
+            eps = __fdiv_rn(__fsub_rn(rax, x0), rm1);
+        }
+        float xn;
+        if (last != 0.0f) {
+            xn = x0;
+        } else {
+            xn = __fadd_rn(__fmul_rn(x0, k2), __fmul_rn(k3, eps));
+            if (sigma != 0.0f) xn = __fadd_rn(xn, __fmul_rn(sigma, noise != nullptr ? noise[i] : z[j]));
+            if (guide != nullptr) {
+                const float gt = __fadd_rn(__fmul_rn(sac, guide[i]), __fmul_rn(s1m, gnoise != nullptr ? gnoise[i] : zg[j]));
+                const float m = mask[i];
+                xn = __fadd_rn(__fmul_rn(xn, m), __fmul_rn(gt, __fsub_rn(1.0f, m)));
+            }
+        }
+        x[i] = xn;
+        if (x0_out != nullptr) x0_out[i] = x0;
+    }
+}
+
 // Ancestral step of LearnedGaussianDiffusion (learned_gaussian_diffusion.py:91-111 + dd:638-645): the network output has
 // 2C channels per sample, (pred_noise | variance interpolation fraction v in [-1, 1]):
 //   logvar = f * log(beta_t) + (1 - f) * posterior_log_variance_clipped_t,  f = (v + 1) / 2
@@ -509,6 +562,13 @@ void launch_sampler_step_learned(float* x, const float* mo, const float* noise, 
                                  int* step_counter, int advance, unsigned long long seed, long long numel, long long per_sample, cudaStream_t s) {
     sampler_step_learned_kernel<<<blocks_for((numel + 3) / 4, 256), 256, 0, s>>>(x, mo, noise, noise_stride, x0_out, coef, step_counter, seed,
                                                                                   numel, per_sample);
+    if (advance) bump_counter_kernel<<<1, 1, 0, s>>>(step_counter);
+}
+void launch_sampler_step_guided(float* x, const float* mo, const float* noise, long long noise_stride, const float* guide, const float* mask,
+                                const float* gnoise, long long gnoise_stride, float* x0_out, const float* coef, int* step_counter, int advance,
+                                int objective, int clip, unsigned long long seed, long long numel, cudaStream_t s) {
+    sampler_step_guided_kernel<<<blocks_for((numel + 3) / 4, 256), 256, 0, s>>>(x, mo, noise, noise_stride, guide, mask, gnoise, gnoise_stride,
+                                                                                 x0_out, coef, step_counter, objective, clip, seed, numel);
     if (advance) bump_counter_kernel<<<1, 1, 0, s>>>(step_counter);
 }
 void launch_finalize(const float* x, float* y, int unnorm, long long numel, cudaStream_t s) {

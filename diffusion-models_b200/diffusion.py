@@ -214,11 +214,22 @@ class DenoisingDiffusion(nn.Module):
             rows[i, 6], rows[i, 7] = sac[t], s1m[t]
         return rows
 
+    @staticmethod
+    def _rank() -> int:
+        return torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+
     def _next_seed(self) -> int:
+        """Key of a cached loop's in-kernel Philox stream (a launch argument baked into the captured graph)."""
         self._seed_calls += 1
-        return (torch.initial_seed() * 1000003 + self._seed_calls * 7919 + 17 * torch.distributed.get_rank()
-                if torch.distributed.is_available() and torch.distributed.is_initialized()
-                else torch.initial_seed() * 1000003 + self._seed_calls * 7919) % (2 ** 63)
+        return (torch.initial_seed() * 1000003 + self._seed_calls * 7919 + 17 * self._rank()) % (2 ** 63)
+
+    def _call_salt(self) -> int:
+        """One draw per sampling call from torch's (CPU) default generator: like the reference, a call is reproducible after
+        `torch.manual_seed(s)` and differs from the previous call otherwise.  It seeds the call's x_T and, through the device
+        counter's second slot, salts the step noise of a replayed graph; the rank is mixed in so that the ranks of a sharded
+        run draw different samples under the same `manual_seed` (the usual torchrun pattern)."""
+        base = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        return (base * 2654435761 + self._rank() * 40503 + 1) % (2 ** 62)
 
     # ------------------------------------------------------------------ the fused loop
     @torch.no_grad()
@@ -239,8 +250,17 @@ class DenoisingDiffusion(nn.Module):
         lib = eng.lib
         stream = torch.cuda.current_stream(dev)
 
-        if x_T is None:
-            x_T = torch.randn(shape, device=dev)                                  # dd:651,676
+        salt = self._call_salt()
+        if x_T is None:                                                           # dd:651,676
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(salt)
+            x_T = torch.randn(shape, device=dev, generator=gen)
+        # a conditional network must be given its condition: the engine buffers would otherwise still hold the previous
+        # call's (or zeros), silently
+        if eng.cond is not None and cond is None:
+            raise ValueError("this model is image-conditional: pass cond=")
+        if eng.text is not None and text_emb is None:
+            raise ValueError("this model is text-conditional: pass text_emb=")
         if cond is not None:
             eng.cond.copy_(cond)
         if text_emb is not None and eng.text is not None:
@@ -271,8 +291,8 @@ class DenoisingDiffusion(nn.Module):
             if cacheable:
                 eng.loops[key] = loop
         coef_dev, counter, ss_table, seed = loop["coef_dev"], loop["counter"], loop["ss_table"], loop["seed"]
-        loop["epoch"] += 1
-        counter.copy_(torch.tensor([0, loop["epoch"] & 0x7FFFFFFF], dtype=torch.int32))
+        loop["epoch"] = salt & 0x7FFFFFFF
+        counter.copy_(torch.tensor([0, loop["epoch"]], dtype=torch.int32))
 
         noise_ptr, noise_stride = None, 0
         if step_noise is not None:
@@ -319,7 +339,7 @@ class DenoisingDiffusion(nn.Module):
             if loop["graph"] is None:
                 eng.x.copy_(x_T)                                  # warm-up launch outside capture, then restore state
                 step_ops(stream.cuda_stream)
-                counter.copy_(torch.tensor([0, loop["epoch"] & 0x7FFFFFFF], dtype=torch.int32))
+                counter.copy_(torch.tensor([0, loop["epoch"]], dtype=torch.int32))
                 if eng.x_self_cond is not None:
                     eng.x_self_cond.zero_()
                 graph = torch.cuda.CUDAGraph()
@@ -378,10 +398,11 @@ class DenoisingDiffusion(nn.Module):
         return a * x_start + b * noise
 
     @torch.no_grad()
-    def interpolate(self, x1, x2, t=None, lam=0.5, *, q_noise=None, step_noise=None, use_graph=True):
+    def interpolate(self, x1, x2, t=None, lam=0.5, *, q_noise=None, step_noise=None, use_graph=True, cond=None, text_emb=None):
         """dd:785-803: both images noised to step `t`, blended with weight `lam`, then ancestral steps t-1 .. 0 on the
         B200 path.  Like the reference, inputs are taken as already normalised and the result is returned raw.
-        Keyword-only extras: `q_noise` = (noise for x1, noise for x2), `step_noise` = per-step draws (parity mode)."""
+        Keyword-only extras: `q_noise` = (noise for x1, noise for x2), `step_noise` = per-step draws (parity mode),
+        `cond` / `text_emb` = the condition of a conditional model (the subclasses put it in the reference's position)."""
         assert x1.shape == x2.shape
         t = self.num_timesteps - 1 if t is None else int(t)
         tb = torch.full((x1.shape[0],), t, device=x1.device, dtype=torch.long)
@@ -389,7 +410,7 @@ class DenoisingDiffusion(nn.Module):
         img = (1 - lam) * self.q_sample(x1, tb, n1) + lam * self.q_sample(x2, tb, n2)
         times = list(reversed(range(0, t)))
         return self._run_loop(_KIND_DDPM, tuple(img.shape), times, self._ddpm_coefs(times), x_T=img.float().contiguous(),
-                              step_noise=step_noise, use_graph=use_graph, raw=True)
+                              step_noise=step_noise, use_graph=use_graph, raw=True, cond=cond, text_emb=text_emb)
 
     @torch.no_grad()
     def sample(self, batch_size=16, return_all_timesteps=False, **kw):

@@ -42,6 +42,12 @@ def sample_sharded(sample_fn: Callable[[int, int], torch.Tensor], batch_size: in
     if not (dist.is_available() and dist.is_initialized()):
         return sample_fn(batch_size, 0)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if batch_size < world:
+        # some ranks would get an empty slice: they cannot run the sampler (B = 0) and have no shape to contribute, so
+        # rank 0's block defines the shape: every rank samples ONE row and the first `batch_size` rows are kept
+        bounds = [(r, r + 1) for r in range(world)]
+        local = sample_fn(1, rank)
+        return gather_samples(local, bounds, group)[:batch_size]
     bounds = shard_bounds(batch_size, world)
     lo, hi = bounds[rank]
     local = sample_fn(hi - lo, rank)

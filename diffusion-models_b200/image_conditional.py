@@ -89,6 +89,13 @@ class ImageConditionalDenoisingDiffusion(DenoisingDiffusion):
         return self.p_sample_loop(shape, return_condition_image, return_all_timesteps=return_all_timesteps, **kw)
 
     @torch.no_grad()
+    def interpolate(self, x1, x2, t=None, cond=None, lam=0.5, **kw):
+        """ic:232-249 (same positional order: x1, x2, t, cond, lam)."""
+        if cond is None:
+            raise ValueError("interpolate() of an image-conditional model needs cond")
+        return super().interpolate(x1, x2, t, lam, cond=self._prepare_cond(cond, x1.shape[0]), **kw)
+
+    @torch.no_grad()
     def p_sample(self, x, t: int, cond=None, x_self_cond=None):
         """ic:114-121."""
         return super().p_sample(x, t, x_self_cond, cond=cond)

@@ -108,6 +108,13 @@ class TextConditionalDenoisingDiffusion(DenoisingDiffusion):
         return fn((batch_size, channels, h, w), save_path_for_text, return_all_timesteps=return_all_timesteps, **kw)
 
     @torch.no_grad()
+    def interpolate(self, x1, x2, t=None, text_emb=None, lam=0.5, **kw):
+        """tc:456-473 (same positional order: x1, x2, t, text_emb, lam)."""
+        if text_emb is None:
+            raise ValueError("interpolate() of a text-conditional model needs text_emb")
+        return super().interpolate(x1, x2, t, lam, text_emb=text_emb, **kw)
+
+    @torch.no_grad()
     def p_sample(self, x, t: int, text_emb=None, x_self_cond=None):
         """tc:309-316."""
         return super().p_sample(x, t, x_self_cond, text_emb=text_emb)

@@ -192,6 +192,16 @@ int ddm_sampler_step(int kind, float* x, const float* model_out, const float* no
 int ddm_sampler_step_learned(float* x, const float* model_out, const float* noise, long long noise_step_stride, float* x_start_out,
                              const float* coef, int* step_counter, int advance, unsigned long long seed, long long numel,
                              long long per_sample, void* stream);
+/* Guided DDIM step (dd:710-777 ddim_sample_guided): x0 / eps as model_predictions returns them with
+ * clip_x_start = clip_denoised and WITHOUT re-deriving eps, the DDIM update of the DDIM row above, then (not on the
+ * last step) the known region is overwritten with the guide noised to step t (dd:747-749):
+ *   x = x * mask + (sqrt_acp[t] * guide + sqrt_1m_acp[t] * z_g) * (1 - mask)
+ * guide, mask: fp32, `numel` elements each (mask already broadcast), or both NULL (plain unguided loop);
+ * guide_noise: injected z_g per step (parity mode) or NULL to draw it in-kernel. */
+int ddm_sampler_step_guided(float* x, const float* model_out, const float* noise, long long noise_step_stride, const float* guide,
+                            const float* mask, const float* guide_noise, long long guide_noise_step_stride, float* x_start_out,
+                            const float* coef, int* step_counter, int advance, int objective, int clip_denoised, unsigned long long seed,
+                            long long numel, void* stream);
 /* y = (x + 1) * 0.5 (utils.py:48-49) or a plain copy when unnormalize == 0 */
 int ddm_finalize(const float* x, float* y, int unnormalize, long long numel, void* stream);
 /* dst[i] = src[(*step_counter) * row_len + i]: selects the current step's row of a precomputed per-step table */

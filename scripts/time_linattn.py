@@ -17,7 +17,11 @@ def main():
     lib = _lib.init(0)
     g = torch.Generator().manual_seed(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for B, n in ((1024, 1024), (1024, 256), (256, 4096), (64, 16384), (128, 1024)):
+    shapes = ((1024, 1024), (1024, 256), (256, 4096), (64, 16384), (128, 1024))
+    if len(sys.argv) > 2:
+        shapes = ((int(sys.argv[1]), int(sys.argv[2])),)
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+    for B, n in shapes:
         C_, heads, d = 64, 4, 32
         hid = heads * d
         x = torch.randn((B, n, C_), generator=g).to("cuda", torch.bfloat16)
@@ -35,7 +39,7 @@ def main():
         a.heads, a.dim_head, a.n_mem = heads, d, 4
         s = torch.cuda.current_stream().cuda_stream
         ts = []
-        for i in range(25):
+        for i in range(reps):
             flush.fill_(i & 1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -43,7 +47,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
-        ts = sorted(ts[5:])
+        ts = sorted(ts[min(5, reps - 1):])
         us = ts[len(ts) // 2]
         gb = 2 * x.numel() * 2 / us / 1e3
         print(f"fused linattn block B={B} n={n} C={C_}: {us:8.1f} us   {gb:7.1f} GB/s algorithmic (x read + y write)", flush=True)

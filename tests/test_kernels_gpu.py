@@ -90,6 +90,17 @@ def run_conv(lib, srcs, pk, domain, out, **kw):
 
 
 # ------------------------------------------------------------------------------------------------ conv kernel
+def test_conv_wide_output_1024(lib):
+    """C_out = 1024 (Unet(dim=128, dim_mults=(1,2,4,8)) bottleneck): four N tiles of 256."""
+    from diffusion_models_b200.packing import pack_conv
+    x = dev(rnd((4, 4, 4, 256), 301), BF)
+    pk = pack_conv(rnd((1024, 256, 3, 3), 302, 0.02))
+    bias = dev(rnd((1024,), 303, 0.1))
+    out = torch.zeros((4, 4, 4, 1024), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (4, 4, 4), out, bias=bias)
+    close(out, ref)
+
+
 def test_gemm_1x1_plain(lib):
     from diffusion_models_b200.packing import pack_conv
     x = dev(rnd((2, 16, 16, 64), 1), BF)
