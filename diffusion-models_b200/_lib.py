@@ -74,6 +74,7 @@ EXPORTS = {
                                        C.c_void_p]),
     "ddm_linear_attention_block_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ddm_linear_attention_block": (C.c_int, [C.POINTER(LinAttnBlockArgs), C.c_void_p]),
+    "ddm_debug_linattn_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "ddm_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ddm_sampler_step": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,

@@ -16,7 +16,8 @@
 namespace ddm {
 void launch_linattn_fused(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmWqkv, const CUtensorMap& tmWout,
                           const float* bias_out, const float* g_out, const float* mem_kv, const float* k_shift, int B, int n, int C,
-                          int n_mem, int num_sms, cudaStream_t s);
+                          int n_mem, int num_sms, int trace, cudaStream_t s);
+int linattn_trace_read(long long* host, int cap);
 }
 
 namespace {
@@ -25,6 +26,7 @@ PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 0;
 bool g_ready = false;
 int g_conv_debug = 0;
+int g_laf_trace = 0;
 std::atomic<long long> g_launches{0};
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -109,6 +111,7 @@ static int init_on_current_device(int device) {
     if (r != 0) return r;
     r = ddm::linattn_fused_prepare_attributes();
     if (r != 0) return r;
+    if (const char* t = std::getenv("DDM_LAF_TRACE")) g_laf_trace = std::atoi(t);       // scripts/laf_trace.py
     if (const char* dbg = std::getenv("DDM_CONV_DEBUG")) g_conv_debug = std::atoi(dbg);   // bottleneck bisection, see conv_tc.cuh
     g_ready = true;
     return 0;
@@ -378,6 +381,9 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
 /* debugging aid, not part of the documented ABI surface: drains the conv kernel's device-side event trace */
 int ddm_debug_conv_trace(long long* host_pairs, int cap) { return ddm::conv_trace_read(host_pairs, cap); }
 
+/* debugging aid: drains the fused linear-attention kernel's event trace as (role, tag, clock) triples */
+int ddm_debug_linattn_trace(long long* host_triples, int cap) { return ddm::linattn_trace_read(host_triples, cap); }
+
 int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* weight,
                   const float* bias, void* out_bf16, int B, int H, int W, int Cout, int ksize, void* stream) {
     if (!g_ready) return DDM_E_NOT_INITIALISED;
@@ -481,7 +487,7 @@ int ddm_linear_attention_block(const ddm_linattn_block_args* a, void* stream) {
         if (r != 0) return r;
     }
     ddm::launch_linattn_fused(tmX, tmY, tmWqkv, tmWout, a->bias_out, a->g_out, a->mem_kv, a->k_shift, a->B, a->n, a->C, a->n_mem,
-                              g_num_sms, as_stream(stream));
+                              g_num_sms, g_laf_trace, as_stream(stream));
     return finish(1);
 }
 

@@ -6,7 +6,7 @@
 // HBM traffic is one read of x and one write of y (x is read a second time in pass 2, from L2); the 384-channel qkv
 // tensor, the attention output and the to_out result never leave the SM.
 //
-// One CTA per image (persistent over images): 8 epilogue warps + 1 control warp.  The control warp issues every TMA
+// One CTA per image (persistent over images): 16 epilogue warps + 1 control warp.  The control warp issues every TMA
 // load / store and every MMA and hears from the epilogue warps through mbarriers; MMAs for the NEXT step are issued
 // before the epilogue of the current one finishes (two accumulator buffers), so the tensor pipe runs under the math.
 //
@@ -37,9 +37,11 @@ constexpr int kTileTok = 128;    // tokens per x tile
 constexpr int kChunkTok = 64;    // tokens per pass-1 chunk
 constexpr int kCtxN = 144;       // context accumulator columns (128 + the ones row padded to a multiple of 16)
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = kEpiThreads + 32;     // + the control warp
+// named barriers: 0 = __syncthreads, 1 = epilogue warps only, the rest = epilogue -> control hand-overs
+constexpr int kBarEpi = 1, kBarEdone = 2, kBarYdone = 4, kBarCdone = 6, kBarMtdone = 7;
 
 struct LaParams {
     const float* bias_out;   // [C]
@@ -47,7 +49,11 @@ struct LaParams {
     const float* mem_kv;     // [2][4][32][n_mem]
     const float* k_shift;    // [128] per-channel softmax shift (>= max k)
     int B, n, n_mem;
+    int trace;               // debugging (env DDM_LAF_TRACE): CTA 0 records (event, clock64) pairs, see scripts/laf_trace.py
 };
+
+constexpr int kLafTraceCap = 4096;
+__device__ long long g_laf_trace[2 * kLafTraceCap * 2];      // [role: 0 control, 1 epilogue warp 0][event][tag, clock]
 
 struct alignas(8) LaBars {
     uint64_t xfull[4];
@@ -55,9 +61,6 @@ struct alignas(8) LaBars {
     uint64_t pvdone[2];      // pass 1: context MMA finished reading P/V buffer
     uint64_t yfull[2];       // pass 2: Y tile ready
     uint64_t wfull, woutfull, mdone;
-    uint64_t edone[2];       // epilogue -> control: pass 1 P/V chunk written (acc read out); pass 2 softmax(q) tile written
-    uint64_t ydone[2];       // epilogue -> control: y tile written in place over the x tile
-    uint64_t cdone, mtdone;
     uint32_t tmem_base;
 };
 
@@ -85,8 +88,8 @@ struct LaSmem {
     static constexpr int off_g = off_bias + C * 4;                    // [C]
     static constexpr int off_pm = off_g + C * 4;                      // [128][4] exp(mem_k - shift)
     static constexpr int off_mv = off_pm + 128 * 16;                  // [128][4] mem_v
-    static constexpr int off_red = off_mv + 128 * 16;                 // [2 tiles][2 halves][128]
-    static constexpr int off_bars = off_red + 2 * 2 * 128 * 4;
+    static constexpr int off_red = off_mv + 128 * 16;                 // [2 tiles][4 parts][128]
+    static constexpr int off_bars = off_red + 2 * 4 * 128 * 4;
     static constexpr int kTotal = off_bars + static_cast<int>(sizeof(LaBars));
     static_assert(kTotal + 1024 <= 227 * 1024, "shared-memory plan does not fit");
     static_assert(kUBytes >= 65536, "union region must hold two Qs buffers");
@@ -103,12 +106,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
 template <int C>
 __global__ void __launch_bounds__(kThreads, 1)
 linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
@@ -133,7 +130,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int lane = tid & 31;
     const int q = warp & 3;            // TMEM lane quarter of this warp
-    const int half = warp >> 2;        // column half handled by this warp
+    const int part = (warp >> 2) & 3;  // column quarter handled by this (epilogue) warp
     const int row = q * 32 + lane;     // accumulator row of this thread (channel in pass 1, token in pass 2)
     const int sw = row & 7;
 
@@ -147,9 +144,6 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_init(&bars->wfull, 1);
         mbar_init(&bars->woutfull, 1);
         mbar_init(&bars->mdone, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->edone[i], kEpiWarps); mbar_init(&bars->ydone[i], kEpiWarps); }
-        mbar_init(&bars->cdone, kEpiWarps);
-        mbar_init(&bars->mtdone, kEpiWarps);
         fence_barrier_init();
         prefetch_tmap(&tmX);
         prefetch_tmap(&tmY);
@@ -177,6 +171,16 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float mcl = __ldg(p.k_shift + (row & 127)) * kLog2e;       // pass 1: this thread's channel
 
+    const bool tr_on = p.trace != 0 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kEpiWarps);
+    int tr_n = 0;
+    auto TR = [&](int ev, int idx) {
+        if (tr_on && tr_n < kLafTraceCap) {
+            long long* dst = g_laf_trace + (static_cast<size_t>(warp == 0 ? 1 : 0) * kLafTraceCap + tr_n) * 2;
+            dst[0] = (static_cast<long long>(ev) << 32) | static_cast<unsigned>(idx);
+            dst[1] = clock64();
+            ++tr_n;
+        }
+    };
     auto wait_leader = [&](uint64_t* bar, uint32_t parity) {    // one polling lane per warp
         if (lane == 0) mbar_wait(bar, parity);
         __syncwarp();
@@ -271,9 +275,13 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
             __syncwarp();
         };
-        uint32_t ph_e = 0, ph_yd = 0, ph_misc = 0;       // phase bits of the barriers this warp waits on
-        auto wait_edone = [&](int i) { wait_leader(&bars->edone[i], (ph_e >> i) & 1u); ph_e ^= 1u << i; tc_fence_after(); };
-        auto wait_ydone = [&](int i) { wait_leader(&bars->ydone[i], (ph_yd >> i) & 1u); ph_yd ^= 1u << i; tc_fence_after(); };
+        // Epilogue -> control hand-overs are named barriers (the 512 epilogue threads bar.arrive, this warp bar.syncs):
+        // every mbarrier poller slows the CTA's other mbarrier traffic, and with 16 + 1 polling warps a wait on an already
+        // completed phase took ~700 cycles.  Two ids per event, alternating with the buffer, because the epilogue warps may
+        // arrive for step i + 1 before this warp has consumed step i (never for i + 2: that needs an MMA issued after it).
+        uint32_t ph_misc = 0;
+        auto wait_edone = [&](int i) { named_bar_sync(kBarEdone + i, kThreads); tc_fence_after(); };
+        auto wait_ydone = [&](int i) { named_bar_sync(kBarYdone + i, kThreads); tc_fence_after(); };
 
         // W_out [C][128] is loaded into the M^T region for every image (16 KB from L2, issued as soon as the previous image's
         // last Y MMA has read M^T): the M GEMM reads it before the epilogue warps overwrite the region with M^T
@@ -303,14 +311,19 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             wait_x(G);
             tc_fence_after();
             issue_kv(G, 0);
+            TR(10, 0);
             for (int j = 0; j < J; ++j) {
                 if (j + 1 < J) {
                     const int gt = G + ((j + 1) >> 1);
                     if (((j + 1) & 1) == 0) wait_x(gt);
+                    TR(9, j + 1);
                     issue_kv(gt, j + 1);        // its accumulator was released by epilogue j - 1 (edone waited below)
+                    TR(10, j + 1);
                 }
                 wait_edone(j & 1);              // P/V of chunk j written, accumulator j & 1 read out
+                TR(11, j);
                 issue_ctx(j);
+                TR(12, j);
                 if (j & 1) {                    // both chunks of tile j >> 1 multiplied (epilogue j saw accfull) and its norms taken
                     if (stores_in_flight) { if (elect_one()) bulk_wait_group_read<0>(); __syncwarp(); stores_in_flight = 0; }
                     released = G + (j >> 1) + 1;
@@ -318,7 +331,8 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 }
             }
             // ---- between the passes: M[(h,d)][c] = ctx[(h,d)][(h',e)] . W_out[c][(h',e)]^T   (W_out sits in the M^T region)
-            wait_leader(&bars->cdone, ph_misc & 1u);          // block-diagonal context written (every context MMA retired)
+            named_bar_sync(kBarCdone, kThreads);              // block-diagonal context written (every context MMA retired)
+            TR(30, it);
             wait_leader(&bars->woutfull, ph_misc & 1u);
             tc_fence_after();
             if (elect_one()) {
@@ -332,7 +346,9 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 umma_commit(&bars->mdone);
             }
             __syncwarp();
-            wait_leader(&bars->mtdone, ph_misc & 1u);         // M^T written, its accumulator read out
+            TR(31, it);
+            named_bar_sync(kBarMtdone, kThreads);             // M^T written, its accumulator read out
+            TR(32, it);
             ph_misc ^= 1u;
             tc_fence_after();
             // ---- pass 2
@@ -344,10 +360,14 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     wait_x(G2 + t + 1);
                     issue_q(G2 + t + 1, t + 1);     // its accumulator was released by epilogue Q t - 1
                 }
+                TR(20, t);
                 wait_edone(t & 1);                  // softmax(q) tile written
+                TR(21, t);
                 issue_y(t);                         // its accumulator was released by epilogue Y t - 2 (ydone waited below)
+                TR(22, t);
                 if (t >= 1) {
                     wait_ydone((t - 1) & 1);
+                    TR(23, t - 1);
                     if (elect_one()) {
                         // the previous store has read its tile by now: hand that buffer back to the loader first
                         if (stores_in_flight) bulk_wait_group_read<0>();
@@ -378,240 +398,274 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         __syncwarp();
     } else {
         // =============================================================================================== epilogue warps
-        auto wait_x = [&](int g) { wait_leader(&bars->xfull[g % NB], static_cast<uint32_t>(g / NB) & 1u); };
-        auto arrive = [&](uint64_t* bar) {     // this warp's generic-proxy writes / TMEM reads are done
+        // 16 warps: q = warp & 3 is the TMEM lane quarter (accumulator rows 32q .. 32q+31), part = warp >> 2 the column
+        // quarter.  Four warps per scheduler: the math of one warp hides the TMEM / shared-memory / MUFU latencies of the
+        // others (with 8 warps the kernel was latency-bound at one instruction per 7.7 cycles per warp).
+        const float* rn_f = rn_s;
+        const float* rnl_f = rnl_s;
+        const bool leader = warp == 0 && lane == 0;       // the only mbarrier poller among the epilogue warps
+        auto arrive = [&](int bar_id) {     // this thread's generic-proxy writes / TMEM reads are done: tell the control warp
             fence_proxy_async();
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar);
+            named_bar_arrive(bar_id, kThreads);
         };
-        // per-token 1 / max(||x||, 1e-12) of tile g (the block's pre-norm, dd:176; gain is folded into W_qkv)
+        auto xbar = [&](int g) -> uint64_t* { return &bars->xfull[g % NB]; };
+        auto xpar = [&](int g) -> uint32_t { return static_cast<uint32_t>(g / NB) & 1u; };
+        // per-token 1 / max(||x||, 1e-12) of tile g (the block's pre-norm, dd:176; gain is folded into W_qkv):
+        // four lanes per token, two 16-byte units each
         auto rn_compute = [&](int g) {
-            if (tid < kTileTok) {
-                const int slot = g % NB;
-                float ss = 0.0f;
+            const int slot = g % NB;
+            const int r = warp * 8 + (lane >> 2), sub = lane & 3;
+            float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-                for (int a = 0; a < kAtoms; ++a) {
-                    const uint32_t base = sb + L::off_x + slot * L::kXTile + a * (kTileTok * 128) + tid * 128;
+            for (int a = 0; a < kAtoms; ++a) {
+                const uint32_t base = sb + L::off_x + slot * L::kXTile + a * (kTileTok * 128) + r * 128;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const uint4 v = lds_128u(base + static_cast<uint32_t>((u ^ (tid & 7)) << 4));      // any order: it is a sum
-                        ss = fmaf(bf16_lo(v.x), bf16_lo(v.x), ss); ss = fmaf(bf16_hi(v.x), bf16_hi(v.x), ss);
-                        ss = fmaf(bf16_lo(v.y), bf16_lo(v.y), ss); ss = fmaf(bf16_hi(v.y), bf16_hi(v.y), ss);
-                        ss = fmaf(bf16_lo(v.z), bf16_lo(v.z), ss); ss = fmaf(bf16_hi(v.z), bf16_hi(v.z), ss);
-                        ss = fmaf(bf16_lo(v.w), bf16_lo(v.w), ss); ss = fmaf(bf16_hi(v.w), bf16_hi(v.w), ss);
-                    }
+                for (int k = 0; k < 2; ++k) {
+                    const uint4 v = lds_128u(base + static_cast<uint32_t>(((2 * sub + k) ^ (r & 7)) << 4));      // any order: it is a sum
+                    s0 = fmaf(bf16_lo(v.x), bf16_lo(v.x), s0); s1 = fmaf(bf16_hi(v.x), bf16_hi(v.x), s1);
+                    s0 = fmaf(bf16_lo(v.y), bf16_lo(v.y), s0); s1 = fmaf(bf16_hi(v.y), bf16_hi(v.y), s1);
+                    s0 = fmaf(bf16_lo(v.z), bf16_lo(v.z), s0); s1 = fmaf(bf16_hi(v.z), bf16_hi(v.z), s1);
+                    s0 = fmaf(bf16_lo(v.w), bf16_lo(v.w), s0); s1 = fmaf(bf16_hi(v.w), bf16_hi(v.w), s1);
                 }
+            }
+            float ss = s0 + s1;
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            if (sub == 0) {
                 const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-                rn_s[slot * 128 + tid] = rn;
-                rnl_s[slot * 128 + tid] = rn * kLog2e;
+                rn_s[slot * 128 + r] = rn;
+                rnl_s[slot * 128 + r] = rn * kLog2e;
             }
         };
-        uint32_t ph_acc = 0, ph_pv = 0, ph_y = 0, ph_m = 0;     // phase bits, one per barrier
-        auto wait_acc = [&](int i) { wait_leader(&bars->accfull[i], (ph_acc >> i) & 1u); ph_acc ^= 1u << i; tc_fence_after(); };
-        auto wait_pv = [&](int i) { wait_leader(&bars->pvdone[i], (ph_pv >> i) & 1u); ph_pv ^= 1u << i; };
-        auto wait_y = [&](int i) { wait_leader(&bars->yfull[i], (ph_y >> i) & 1u); ph_y ^= 1u << i; tc_fence_after(); };
+        uint32_t ph_acc = 0, ph_pv = 0, ph_y = 0, ph_m = 0;     // phase bits, one per barrier (tracked by every thread, used by the leader)
+        auto poll_acc = [&](int i) { if (leader) mbar_wait(&bars->accfull[i], (ph_acc >> i) & 1u); ph_acc ^= 1u << i; };
+        auto poll_pv = [&](int i) { if (leader) mbar_wait(&bars->pvdone[i], (ph_pv >> i) & 1u); ph_pv ^= 1u << i; };
+        auto poll_y = [&](int i) { if (leader) mbar_wait(&bars->yfull[i], (ph_y >> i) & 1u); ph_y ^= 1u << i; };
+        auto poll_x = [&](int g) { if (leader) mbar_wait(xbar(g), xpar(g)); };
+        auto publish = [&]() { named_bar_sync(kBarEpi, kEpiThreads); tc_fence_after(); };     // what the leader saw holds for all
 
         int G = 0;       // global tile index of the current image's first pass-1 tile
         for (int it = 0; it < n_img; ++it, G += 2 * T) {
             // ======================================================================================= pass 1
-            {   // the V^T buffers' extra rows: row 128 = ones (its context column is the sum of P), rows 129..143 = 0
+            if (tid < 256) {   // the V^T buffers' extra rows: row 128 = ones (its context column is the sum of P), rows 129..143 = 0
                 const int vb = tid >> 7, r = (tid & 127) >> 3, u = tid & 7;
                 const uint32_t one2 = r == 0 ? 0x3F803F80u : 0u;
                 sts_128u(sb + L::off_u + 2 * L::kPBytes + vb * L::kVBytes + (128 + r) * 128 + u * 16, one2, one2, one2, one2);
                 // published to the context MMA by the fence + arrival that follows chunk 0 (edone)
             }
+            poll_x(G);
+            publish();
+            rn_compute(G);            // published by the barrier that opens chunk 0
             for (int j = 0; j < J; ++j) {
                 const int gt = G + (j >> 1);
-                if ((j & 1) == 0) {
-                    wait_x(gt);
-                    rn_compute(gt);
-                    named_bar_sync(1, kEpiThreads);
-                }
-                wait_acc(j & 1);
-                if (j >= 2) wait_pv(j & 1);
-                {   // epilogue: thread = channel `row`; tokens half*32 .. +31 of the chunk
+                if ((j & 1) && j + 1 < J) poll_x(gt + 1);      // the next tile, for its norms at the end of this chunk
+                poll_acc(j & 1);
+                if (j >= 2) poll_pv(j & 1);
+                publish();
+                TR(4, j);
+                {   // epilogue: thread = channel `row`; tokens part*16 .. +15 of the chunk
                     const int slot = gt % NB;
-                    const uint32_t accb = t_lane + static_cast<uint32_t>((j & 1) * 128 + half * 32);
-                    uint32_t kr[32], vr[32];
-                    tmem_ld32(accb, kr);
-                    tmem_ld32(accb + 64u, vr);
+                    const uint32_t accb = t_lane + static_cast<uint32_t>((j & 1) * 128 + part * 16);
+                    uint32_t kr[16], vr[16];
+                    tmem_ld16(accb, kr);
+                    tmem_ld16(accb + 64u, vr);
+                    const int tok0 = slot * 128 + (j & 1) * 64 + part * 16;
+                    float al[16], bl[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(rnl_f + tok0 + 4 * i);
+                        const float4 b4 = *reinterpret_cast<const float4*>(rn_f + tok0 + 4 * i);
+                        al[4 * i] = a4.x; al[4 * i + 1] = a4.y; al[4 * i + 2] = a4.z; al[4 * i + 3] = a4.w;
+                        bl[4 * i] = b4.x; bl[4 * i + 1] = b4.y; bl[4 * i + 2] = b4.z; bl[4 * i + 3] = b4.w;
+                    }
                     tmem_ld_wait();
-                    const uint32_t rl = sb + L::off_rnl + (slot * 128 + (j & 1) * 64 + half * 32) * 4;
-                    const uint32_t r1 = sb + L::off_rn + (slot * 128 + (j & 1) * 64 + half * 32) * 4;
                     const uint32_t prow = sb + L::off_u + (j & 1) * L::kPBytes + row * 128;
                     const uint32_t vrow = sb + L::off_u + 2 * L::kPBytes + (j & 1) * L::kVBytes + row * 128;
+                    uint32_t pw[8], vw[8];
 #pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        const float4 a0 = lds_f4(rl + g8 * 32), a1 = lds_f4(rl + g8 * 32 + 16);
-                        const float4 b0 = lds_f4(r1 + g8 * 32), b1 = lds_f4(r1 + g8 * 32 + 16);
-                        const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                        const float bl[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                        uint32_t pw[4], vw[4];
+                    for (int i = 0; i < 8; ++i) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(kr[2 * i]), al[2 * i], -mcl));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(kr[2 * i + 1]), al[2 * i + 1], -mcl));
+                        pw[i] = pack_bf16x2(p0, p1);
+                        vw[i] = pack_bf16x2(__uint_as_float(vr[2 * i]) * bl[2 * i], __uint_as_float(vr[2 * i + 1]) * bl[2 * i + 1]);
+                    }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(kr[g8 * 8 + 2 * i]), al[2 * i], -mcl));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(kr[g8 * 8 + 2 * i + 1]), al[2 * i + 1], -mcl));
-                            pw[i] = pack_bf16x2(p0, p1);
-                            vw[i] = pack_bf16x2(__uint_as_float(vr[g8 * 8 + 2 * i]) * bl[2 * i], __uint_as_float(vr[g8 * 8 + 2 * i + 1]) * bl[2 * i + 1]);
-                        }
-                        const uint32_t uo = static_cast<uint32_t>(((half * 4 + g8) ^ sw) << 4);
-                        sts_128u(prow + uo, pw[0], pw[1], pw[2], pw[3]);
-                        sts_128u(vrow + uo, vw[0], vw[1], vw[2], vw[3]);
+                    for (int g2 = 0; g2 < 2; ++g2) {
+                        const uint32_t uo = static_cast<uint32_t>(((part * 2 + g2) ^ sw) << 4);
+                        sts_128u(prow + uo, pw[4 * g2], pw[4 * g2 + 1], pw[4 * g2 + 2], pw[4 * g2 + 3]);
+                        sts_128u(vrow + uo, vw[4 * g2], vw[4 * g2 + 1], vw[4 * g2 + 2], vw[4 * g2 + 3]);
                     }
                 }
-                arrive(&bars->edone[j & 1]);
+                TR(5, j);
+                arrive(kBarEdone + (j & 1));
+                if ((j & 1) && j + 1 < J) rn_compute(gt + 1);
+                TR(6, j);
             }
-            wait_pv(J & 1);            // chunk J-2
-            wait_pv((J - 1) & 1);      // chunk J-1: the context is complete
-            tc_fence_after();
+            poll_pv(J & 1);            // chunk J-2
+            poll_pv((J - 1) & 1);      // chunk J-1: the context is complete
+            publish();
+            TR(50, it);
 
             // ======================================================================================= between the passes
-            if (half == 0) {    // head q, channel d = lane: context row, normalised, d^-0.5 folded in (dd:187)
-                uint32_t cr[32];
-                tmem_ld32(t_lane + 256u + static_cast<uint32_t>(q * 32), cr);
+            {   // row (h = q, d = lane) of the block-diagonal bf16 context [128][128]: 16 units of 8 columns, this thread writes
+                // units part, part+4, part+8, part+12; exactly one of them (own head, e = 8*part ..) carries data:
+                // (ctx + memory tokens) / sum * d^-0.5   (dd:181-182, 187)
+                uint32_t cr[8];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                             : "=r"(cr[0]), "=r"(cr[1]), "=r"(cr[2]), "=r"(cr[3]), "=r"(cr[4]), "=r"(cr[5]), "=r"(cr[6]), "=r"(cr[7])
+                             : "r"(t_lane + 256u + static_cast<uint32_t>(q * 32 + part * 8))
+                             : "memory");
                 float ksum = __uint_as_float(tmem_ld1(t_lane + 256u + 128u));
                 tmem_ld_wait();
                 const float4 pm = *reinterpret_cast<const float4*>(pm_s + row * 4);
                 ksum += (pm.x + pm.y) + (pm.z + pm.w);
                 const float sc = 0.17677669529663687f / ksum;     // 32^-0.5 / sum
-                const uint32_t crow = sb + L::off_u + (q >> 1) * 16384 + row * 128;
+                uint32_t w[4];
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    uint32_t w[4];
+                for (int i = 0; i < 4; ++i) {
+                    float v[2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float v[2];
-#pragma unroll
-                        for (int e2 = 0; e2 < 2; ++e2) {
-                            const int e = g8 * 8 + 2 * i + e2;
-                            const float4 mv = *reinterpret_cast<const float4*>(mv_s + (q * 32 + e) * 4);     // warp-uniform address
-                            float c = __uint_as_float(cr[e]);
-                            c = fmaf(pm.x, mv.x, c); c = fmaf(pm.y, mv.y, c); c = fmaf(pm.z, mv.z, c); c = fmaf(pm.w, mv.w, c);
-                            v[e2] = c * sc;
-                        }
-                        w[i] = pack_bf16x2(v[0], v[1]);
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                        const int e = part * 8 + 2 * i + e2;
+                        const float4 mv = *reinterpret_cast<const float4*>(mv_s + (q * 32 + e) * 4);     // warp-uniform address
+                        float c = __uint_as_float(cr[2 * i + e2]);
+                        c = fmaf(pm.x, mv.x, c); c = fmaf(pm.y, mv.y, c); c = fmaf(pm.z, mv.z, c); c = fmaf(pm.w, mv.w, c);
+                        v[e2] = c * sc;
                     }
-                    sts_128u(crow + static_cast<uint32_t>((((q & 1) * 4 + g8) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+                    w[i] = pack_bf16x2(v[0], v[1]);
                 }
-            } else {            // the other heads' columns of this row are zero (block-diagonal context)
+                const int own = (q >> 1) * 8 + (q & 1) * 4 + part;       // unit index (atom * 8 + unit) of the data
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (!(a == (q >> 1) && (u >> 2) == (q & 1)))
-                            sts_128u(sb + L::off_u + a * 16384 + row * 128 + static_cast<uint32_t>((u ^ sw) << 4), 0u, 0u, 0u, 0u);
+                for (int k = 0; k < 4; ++k) {
+                    const int U = part + 4 * k;
+                    const uint32_t addr = sb + L::off_u + (U >> 3) * 16384 + row * 128 + static_cast<uint32_t>(((U & 7) ^ sw) << 4);
+                    if (U == own) sts_128u(addr, w[0], w[1], w[2], w[3]);
+                    else sts_128u(addr, 0u, 0u, 0u, 0u);
+                }
             }
-            arrive(&bars->cdone);
-            wait_leader(&bars->mdone, ph_m);
+            arrive(kBarCdone);
+            TR(51, it);
+            if (leader) mbar_wait(&bars->mdone, ph_m);
             ph_m ^= 1u;
-            tc_fence_after();
-            {   // thread = row (h,d) of M; columns c = half * C/2 .. ; stored transposed as M^T[c][(h,d)] (K-major B operand of Y)
-                constexpr int kMc = C / 2;
+            publish();
+            TR(52, it);
+            {   // thread = row (h,d) of M; columns c = part * C/4 .. ; stored transposed as M^T[c][(h,d)] (K-major B operand of Y)
+                constexpr int kMc = C / 4;
+                static_assert(kMc == 16, "M epilogue is written for C = 64");
                 const uint32_t mbase = sb + L::off_mt + (row >> 6) * (C * 128) + static_cast<uint32_t>((row & 7) * 2);
                 const int ku = (row & 63) >> 3;
+                uint32_t mr[16];
+                tmem_ld16(t_lane + static_cast<uint32_t>(part * kMc), mr);
+                tmem_ld_wait();
 #pragma unroll
-                for (int c32 = 0; c32 < kMc / 32; ++c32) {
-                    uint32_t mr[32];
-                    tmem_ld32(t_lane + static_cast<uint32_t>(half * kMc + c32 * 32), mr);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = half * kMc + c32 * 32 + i;
-                        const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(mr[i])));
-                        asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(mbase + c * 128 + static_cast<uint32_t>((ku ^ (c & 7)) << 4)), "h"(hv) : "memory");
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    const int c = part * kMc + i;
+                    const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(mr[i])));
+                    asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(mbase + c * 128 + static_cast<uint32_t>((ku ^ (c & 7)) << 4)), "h"(hv) : "memory");
                 }
             }
-            arrive(&bars->mtdone);
+            arrive(kBarMtdone);
+            TR(53, it);
 
             // ======================================================================================= pass 2
             const int G2 = G + T;
-            auto epilogue_y = [&](int u_t) {
-                wait_y(u_t & 1);
+            auto epilogue_y = [&](int u_t) {     // its yfull was polled and published by the caller
+                TR(45, u_t);
                 const int slot = (G2 + u_t) % NB;
-                constexpr int kCols = C / 2;                      // columns of this thread: half * kCols .. +kCols-1
-                const uint32_t accb = t_lane + 256u + static_cast<uint32_t>((u_t & 1) * 128 + half * kCols);
-                float v[kCols];
-                float ss = 0.0f;
-#pragma unroll
-                for (int c32 = 0; c32 < kCols / 32; ++c32) {
-                    uint32_t yr[32];
-                    tmem_ld32(accb + c32 * 32, yr);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 bb = lds_f4(sb + L::off_bias + (half * kCols + c32 * 32 + i) * 4);
-                        v[c32 * 32 + i] = __uint_as_float(yr[i]) + bb.x;
-                        v[c32 * 32 + i + 1] = __uint_as_float(yr[i + 1]) + bb.y;
-                        v[c32 * 32 + i + 2] = __uint_as_float(yr[i + 2]) + bb.z;
-                        v[c32 * 32 + i + 3] = __uint_as_float(yr[i + 3]) + bb.w;
-                        ss = fmaf(v[c32 * 32 + i], v[c32 * 32 + i], ss);
-                        ss = fmaf(v[c32 * 32 + i + 1], v[c32 * 32 + i + 1], ss);
-                        ss = fmaf(v[c32 * 32 + i + 2], v[c32 * 32 + i + 2], ss);
-                        ss = fmaf(v[c32 * 32 + i + 3], v[c32 * 32 + i + 3], ss);
-                    }
-                }
-                red_s[(u_t & 1) * 256 + half * 128 + row] = ss;
-                named_bar_sync(1, kEpiThreads);
-                const float rinv = 1.0f / fmaxf(sqrtf(red_s[(u_t & 1) * 256 + row] + red_s[(u_t & 1) * 256 + 128 + row]), 1e-12f);
-                // residual x (own row of the tile), result written in place; column c lives in atom c / 64, unit (c % 64) / 8
+                constexpr int kCols = C / 4;                      // columns of this thread: part * kCols .. +kCols-1
+                static_assert(kCols == 16, "Y epilogue is written for C = 64");
+                uint32_t yr[16];
+                tmem_ld16(t_lane + 256u + static_cast<uint32_t>((u_t & 1) * 128 + part * kCols), yr);
+                // residual x (own row of the tile); the result is written in place.  column c: atom c / 64, unit (c % 64) / 8
                 const uint32_t xrow = sb + L::off_x + slot * L::kXTile + row * 128;
+                const uint32_t a0 = xrow + static_cast<uint32_t>(((part * 2) ^ sw) << 4), a1 = xrow + static_cast<uint32_t>(((part * 2 + 1) ^ sw) << 4);
+                const uint4 x0 = lds_128u(a0), x1 = lds_128u(a1);
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + part * kCols);
+                const float4* gp = reinterpret_cast<const float4*>(g_s + part * kCols);
+                float v[16];
+                tmem_ld_wait();
+                float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-                for (int u8 = 0; u8 < kCols / 8; ++u8) {
-                    const int c0 = half * kCols + u8 * 8;
-                    const uint32_t addr = xrow + (c0 >> 6) * (kTileTok * 128) + static_cast<uint32_t>(((((c0 & 63) >> 3)) ^ sw) << 4);
-                    const uint4 xr = lds_128u(addr);
-                    const float4 g0 = lds_f4(sb + L::off_g + c0 * 4), g1 = lds_f4(sb + L::off_g + c0 * 4 + 16);
-                    const float* vv = v + u8 * 8;
-                    const uint32_t w0 = pack_bf16x2(fmaf(vv[0] * rinv, g0.x, bf16_lo(xr.x)), fmaf(vv[1] * rinv, g0.y, bf16_hi(xr.x)));
-                    const uint32_t w1 = pack_bf16x2(fmaf(vv[2] * rinv, g0.z, bf16_lo(xr.y)), fmaf(vv[3] * rinv, g0.w, bf16_hi(xr.y)));
-                    const uint32_t w2 = pack_bf16x2(fmaf(vv[4] * rinv, g1.x, bf16_lo(xr.z)), fmaf(vv[5] * rinv, g1.y, bf16_hi(xr.z)));
-                    const uint32_t w3 = pack_bf16x2(fmaf(vv[6] * rinv, g1.z, bf16_lo(xr.w)), fmaf(vv[7] * rinv, g1.w, bf16_hi(xr.w)));
-                    sts_128u(addr, w0, w1, w2, w3);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 bb = bp[i];
+                    v[4 * i] = __uint_as_float(yr[4 * i]) + bb.x;
+                    v[4 * i + 1] = __uint_as_float(yr[4 * i + 1]) + bb.y;
+                    v[4 * i + 2] = __uint_as_float(yr[4 * i + 2]) + bb.z;
+                    v[4 * i + 3] = __uint_as_float(yr[4 * i + 3]) + bb.w;
+                    s0 = fmaf(v[4 * i], v[4 * i], s0); s1 = fmaf(v[4 * i + 1], v[4 * i + 1], s1);
+                    s0 = fmaf(v[4 * i + 2], v[4 * i + 2], s0); s1 = fmaf(v[4 * i + 3], v[4 * i + 3], s1);
                 }
-                arrive(&bars->ydone[u_t & 1]);
+                float* red = red_s + (u_t & 1) * 512;
+                red[part * 128 + row] = s0 + s1;
+                tc_fence_before();
+                named_bar_sync(kBarEpi, kEpiThreads);
+                TR(46, u_t);
+                const float rinv = 1.0f / fmaxf(sqrtf((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])), 1e-12f);
+                const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
+                sts_128u(a0, pack_bf16x2(fmaf(v[0] * rinv, g0.x, bf16_lo(x0.x)), fmaf(v[1] * rinv, g0.y, bf16_hi(x0.x))),
+                         pack_bf16x2(fmaf(v[2] * rinv, g0.z, bf16_lo(x0.y)), fmaf(v[3] * rinv, g0.w, bf16_hi(x0.y))),
+                         pack_bf16x2(fmaf(v[4] * rinv, g1.x, bf16_lo(x0.z)), fmaf(v[5] * rinv, g1.y, bf16_hi(x0.z))),
+                         pack_bf16x2(fmaf(v[6] * rinv, g1.z, bf16_lo(x0.w)), fmaf(v[7] * rinv, g1.w, bf16_hi(x0.w))));
+                sts_128u(a1, pack_bf16x2(fmaf(v[8] * rinv, g2.x, bf16_lo(x1.x)), fmaf(v[9] * rinv, g2.y, bf16_hi(x1.x))),
+                         pack_bf16x2(fmaf(v[10] * rinv, g2.z, bf16_lo(x1.y)), fmaf(v[11] * rinv, g2.w, bf16_hi(x1.y))),
+                         pack_bf16x2(fmaf(v[12] * rinv, g3.x, bf16_lo(x1.z)), fmaf(v[13] * rinv, g3.y, bf16_hi(x1.z))),
+                         pack_bf16x2(fmaf(v[14] * rinv, g3.z, bf16_lo(x1.w)), fmaf(v[15] * rinv, g3.w, bf16_hi(x1.w))));
+                arrive(kBarYdone + (u_t & 1));
+                TR(47, u_t);
             };
 
+            poll_x(G2);
+            publish();
+            rn_compute(G2);           // published by the barrier that opens tile 0
             for (int t = 0; t < T; ++t) {
-                wait_x(G2 + t);
-                rn_compute(G2 + t);
-                named_bar_sync(1, kEpiThreads);
-                wait_acc(t & 1);
-                {   // epilogue: thread = token `row`; heads 2*half, 2*half+1 -> softmax over the 32 channels of each (dd:184)
+                if (t + 1 < T) poll_x(G2 + t + 1);
+                poll_acc(t & 1);
+                if (t >= 1) poll_y((t - 1) & 1);
+                publish();
+                TR(42, t);
+                {   // epilogue: thread = token `row`, head `part`: softmax over its 32 channels (dd:184)
                     const int slot = (G2 + t) % NB;
-                    const float rnl = rnl_s[slot * 128 + row];
-                    const uint32_t accb = t_lane + static_cast<uint32_t>((t & 1) * 128 + half * 64);
-                    const uint32_t qrow = sb + L::off_u + (t & 1) * 32768 + half * 16384 + row * 128;
+                    const float rnl = rnl_f[slot * 128 + row];
+                    uint32_t qr[32];
+                    tmem_ld32(t_lane + static_cast<uint32_t>((t & 1) * 128 + part * 32), qr);
+                    tmem_ld_wait();
+                    float m0 = fmaxf(__uint_as_float(qr[0]), __uint_as_float(qr[1])), m1 = fmaxf(__uint_as_float(qr[2]), __uint_as_float(qr[3]));
+                    float m2 = fmaxf(__uint_as_float(qr[4]), __uint_as_float(qr[5])), m3 = fmaxf(__uint_as_float(qr[6]), __uint_as_float(qr[7]));
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint32_t qr[32];
-                        tmem_ld32(accb + hh * 32, qr);
-                        tmem_ld_wait();
-                        float m = __uint_as_float(qr[0]);
-#pragma unroll
-                        for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(qr[i]));
-                        const float mm = m * rnl;
-                        float e[32];
-                        float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            e[i] = ex2_approx(fmaf(__uint_as_float(qr[i]), rnl, -mm));
-                            e[i + 1] = ex2_approx(fmaf(__uint_as_float(qr[i + 1]), rnl, -mm));
-                            s0 += e[i];
-                            s1 += e[i + 1];
-                        }
-                        const float inv = 1.0f / (s0 + s1);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            sts_128u(qrow + static_cast<uint32_t>(((hh * 4 + u) ^ sw) << 4),
-                                     pack_bf16x2(e[8 * u] * inv, e[8 * u + 1] * inv), pack_bf16x2(e[8 * u + 2] * inv, e[8 * u + 3] * inv),
-                                     pack_bf16x2(e[8 * u + 4] * inv, e[8 * u + 5] * inv), pack_bf16x2(e[8 * u + 6] * inv, e[8 * u + 7] * inv));
+                    for (int i = 8; i < 32; i += 8) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(qr[i]), __uint_as_float(qr[i + 1])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(qr[i + 2]), __uint_as_float(qr[i + 3])));
+                        m2 = fmaxf(m2, fmaxf(__uint_as_float(qr[i + 4]), __uint_as_float(qr[i + 5])));
+                        m3 = fmaxf(m3, fmaxf(__uint_as_float(qr[i + 6]), __uint_as_float(qr[i + 7])));
                     }
+                    const float mm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * rnl;
+                    float e[32];
+                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        e[i] = ex2_approx(fmaf(__uint_as_float(qr[i]), rnl, -mm));
+                        e[i + 1] = ex2_approx(fmaf(__uint_as_float(qr[i + 1]), rnl, -mm));
+                        e[i + 2] = ex2_approx(fmaf(__uint_as_float(qr[i + 2]), rnl, -mm));
+                        e[i + 3] = ex2_approx(fmaf(__uint_as_float(qr[i + 3]), rnl, -mm));
+                        s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
+                    }
+                    const float inv = 1.0f / ((s0 + s1) + (s2 + s3));
+                    const uint32_t qrow = sb + L::off_u + (t & 1) * 32768 + (part >> 1) * 16384 + row * 128;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        sts_128u(qrow + static_cast<uint32_t>((((part & 1) * 4 + u) ^ sw) << 4),
+                                 pack_bf16x2(e[8 * u] * inv, e[8 * u + 1] * inv), pack_bf16x2(e[8 * u + 2] * inv, e[8 * u + 3] * inv),
+                                 pack_bf16x2(e[8 * u + 4] * inv, e[8 * u + 5] * inv), pack_bf16x2(e[8 * u + 6] * inv, e[8 * u + 7] * inv));
                 }
-                arrive(&bars->edone[t & 1]);
+                TR(43, t);
+                arrive(kBarEdone + (t & 1));
+                TR(44, t);
+                if (t + 1 < T) rn_compute(G2 + t + 1);      // published by epilogue_y's barrier / the next tile's opening barrier
                 if (t >= 1) epilogue_y(t - 1);
             }
+            poll_y((T - 1) & 1);
+            publish();
             epilogue_y(T - 1);
         }
     }
@@ -630,16 +684,29 @@ int linattn_fused_prepare_attributes() {
                                                  LaSmem<64>::kTotal + 1024));
 }
 
+int linattn_trace_read(long long* host, int cap) {
+    static long long tmp[2 * kLafTraceCap * 2];
+    cudaMemcpyFromSymbol(tmp, g_laf_trace, sizeof(tmp));
+    int n = 0;
+    for (int i = 0; i < 2 * kLafTraceCap && n < cap; ++i)
+        if (tmp[2 * i + 1] != 0) { host[3 * n] = i / kLafTraceCap; host[3 * n + 1] = tmp[2 * i]; host[3 * n + 2] = tmp[2 * i + 1]; ++n; }
+    void* sym = nullptr;
+    cudaGetSymbolAddress(&sym, g_laf_trace);
+    cudaMemset(sym, 0, sizeof(tmp));
+    return n;
+}
+
 bool linattn_fused_supported(int C, int n, int heads, int d, int n_mem) {
     return C == 64 && heads == 4 && d == 32 && n >= kTileTok && (n % kTileTok) == 0 && n_mem >= 0 && n_mem <= 4;
 }
 
 void launch_linattn_fused(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmWqkv, const CUtensorMap& tmWout,
                           const float* bias_out, const float* g_out, const float* mem_kv, const float* k_shift, int B, int n, int C,
-                          int n_mem, int num_sms, cudaStream_t s) {
+                          int n_mem, int num_sms, int trace, cudaStream_t s) {
     LaParams p;
     p.bias_out = bias_out; p.g_out = g_out; p.mem_kv = mem_kv; p.k_shift = k_shift;
     p.B = B; p.n = n; p.n_mem = n_mem;
+    p.trace = trace;
     const int grid = B < num_sms ? B : num_sms;
     linattn_fused_kernel<64><<<grid, kThreads, LaSmem<64>::kTotal + 1024, s>>>(tmX, tmY, tmWqkv, tmWout, p);
 }

@@ -143,6 +143,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// non-blocking arrival on a named barrier that other warps bar.sync on (producer side of a one-way hand-over)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ float tanh_approx(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;\n" : "=f"(y) : "f"(x));

@@ -156,6 +156,8 @@ typedef struct ddm_linattn_block_args {
 } ddm_linattn_block_args;
 int ddm_linear_attention_block_supported(int C, int n, int heads, int dim_head, int n_mem);
 int ddm_linear_attention_block(const ddm_linattn_block_args* args, void* stream);
+/* Debugging aid (env DDM_LAF_TRACE=1): drains CTA 0's (role, tag, clock64) event triples; synchronises the device. */
+int ddm_debug_linattn_trace(long long* host_triples, int cap);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K7/K8: softmax attention (dd:220-228 + at:109-124; tc:66-77).  q: bf16 rows [B*nq] with row stride ldq, head h at
