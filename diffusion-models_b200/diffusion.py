@@ -23,6 +23,10 @@ ModelPrediction = namedtuple("ModelPrediction", ["pred_noise", "pred_x_start"])
 _OBJECTIVES = {"pred_noise": 0, "pred_x0": 1, "pred_v": 2}
 
 
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
 def identity(t, *args, **kwargs):
     return t
 
@@ -223,18 +227,19 @@ class DenoisingDiffusion(nn.Module):
         self._seed_calls += 1
         return (torch.initial_seed() * 1000003 + self._seed_calls * 7919 + 17 * self._rank()) % (2 ** 63)
 
-    def _call_salt(self) -> int:
+    @classmethod
+    def _call_salt(cls) -> int:
         """One draw per sampling call from torch's (CPU) default generator: like the reference, a call is reproducible after
         `torch.manual_seed(s)` and differs from the previous call otherwise.  It seeds the call's x_T and, through the device
         counter's second slot, salts the step noise of a replayed graph; the rank is mixed in so that the ranks of a sharded
         run draw different samples under the same `manual_seed` (the usual torchrun pattern)."""
         base = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
-        return (base * 2654435761 + self._rank() * 40503 + 1) % (2 ** 62)
+        return (base * 2654435761 + cls._rank() * 40503 + 1) % (2 ** 62)
 
     # ------------------------------------------------------------------ the fused loop
     @torch.no_grad()
     def _run_loop(self, kind: int, shape, times: Sequence[int], coefs: torch.Tensor, *, x_T=None, step_noise=None,
-                  return_all_timesteps=False, use_graph=True, cond=None, text_emb=None, trace=None, raw=False):
+                  return_all_timesteps=False, use_graph=True, cond=None, text_emb=None, trace=None, raw=False, guided=None):
         """Shared DDIM / DDPM driver: [select scale-shift row -> U-Net plan -> fused update] per step."""
         dev = self.device
         if dev.type != "cuda":
@@ -270,7 +275,7 @@ class DenoisingDiffusion(nn.Module):
             eng.x_self_cond.zero_()
         obj = _OBJECTIVES[self.objective]
         numel = B * C * H * W
-        eager = (not use_graph) or return_all_timesteps or per_sample_time or trace is not None
+        eager = (not use_graph) or return_all_timesteps or per_sample_time or trace is not None or guided is not None
 
         # A loop = device tables (per-step coefficients, per-step scale/shift rows), a {step, epoch} counter and the
         # captured CUDA graph of one step.  It only depends on (engine, sampler kind, objective, timestep list,
@@ -314,7 +319,13 @@ class DenoisingDiffusion(nn.Module):
             else:
                 _lib.check(lib.ddm_select_row(ss_table.data_ptr(), counter.data_ptr(), eng.ss.data_ptr(), eng.ss_width, s))
             eng.run_body(s)
-            if kind == _KIND_DDPM_LEARNED:      # eng.out is [B, 2C, H, W] = (pred_noise | variance fraction)
+            if guided is not None:              # dd:710-777: raw eps, optional clamp, guide blended into the known region
+                _lib.check(lib.ddm_sampler_step_guided(eng.x.data_ptr(), eng.out.data_ptr(), noise_ptr, noise_stride,
+                                                       _p(guided["guide"]), _p(guided["mask"]), _p(guided["guide_noise"]),
+                                                       numel if guided["guide_noise"] is not None else 0, x0_ptr,
+                                                       coef_dev.data_ptr(), counter.data_ptr(), 1, obj, 1 if guided["clip"] else 0,
+                                                       seed, numel, s))
+            elif kind == _KIND_DDPM_LEARNED:    # eng.out is [B, 2C, H, W] = (pred_noise | variance fraction)
                 _lib.check(lib.ddm_sampler_step_learned(eng.x.data_ptr(), eng.out.data_ptr(), noise_ptr, noise_stride, x0_ptr,
                                                         coef_dev.data_ptr(), counter.data_ptr(), 1, seed, numel, C * H * W, s))
             else:
@@ -387,6 +398,34 @@ class DenoisingDiffusion(nn.Module):
         return self._run_loop(_KIND_DDIM, tuple(shape), [t for t, _ in pairs], self._ddim_coefs(pairs, self.ddim_sampling_eta),
                               x_T=noise, step_noise=step_noise, return_all_timesteps=return_all_timesteps,
                               use_graph=use_graph, trace=trace)
+
+    @torch.no_grad()
+    def ddim_sample_guided(self, shape, sampling_timesteps=None, guide=None, mask=None, clip_denoised=True, *, noise=None,
+                           step_noise=None, guide_noise=None, trace=None):
+        """dd:710-777: DDIM that keeps a known region (`mask` == 0) on the guide image: after every non-final update
+        `img = img * mask + q_sample(guide, t) * (1 - mask)`.  Like the reference it uses the network's raw noise prediction
+        (no re-derivation after the x0 clamp), clamps x0 only if `clip_denoised`, and always unnormalises the result.
+        The reference's inline matplotlib display of every step is not reproduced.  Keyword-only extras: `noise` = x_T,
+        `step_noise` / `guide_noise` = per-step draws for the DDIM noise / the guide's q_sample (parity mode)."""
+        S = self.sampling_timesteps if sampling_timesteps is None else sampling_timesteps
+        shape = tuple(shape)
+        dev = self.device
+        pairs = self._ddim_pairs(S)
+        if (guide is None) != (mask is None):
+            raise ValueError("guide and mask go together")
+        g = dict(guide=None, mask=None, guide_noise=None, clip=bool(clip_denoised))
+        if guide is not None:
+            g["guide"] = guide.to(dev, torch.float32).expand(shape).contiguous()
+            g["mask"] = mask.to(dev, torch.float32).expand(shape).contiguous()
+            if guide_noise is not None:
+                gn = guide_noise.to(dev, torch.float32).contiguous()
+                pad = len(pairs) - gn.shape[0]
+                if pad > 0:
+                    gn = torch.cat([gn, torch.zeros((pad,) + shape, device=dev)], dim=0)
+                g["guide_noise"] = gn
+        out = self._run_loop(_KIND_DDIM, shape, [t for t, _ in pairs], self._ddim_coefs(pairs, self.ddim_sampling_eta), x_T=noise,
+                             step_noise=step_noise, trace=trace, raw=True, guided=g)
+        return unnormalize_to_zero_to_one(out)          # dd:776 (unconditionally, also for auto_normalize=False models)
 
     @torch.no_grad()
     def q_sample(self, x_start, t, noise=None):

@@ -20,5 +20,6 @@ from .unet_ref import unet_forward, UnetConfig, infer_config  # noqa: F401
 from .sampler_ref import (  # noqa: F401
     Schedule, make_schedule, ddim_time_pairs, ddim_sample, p_sample_loop,
     model_predictions, ddim_update, ddpm_update, q_sample, interpolate, ddpm_update_learned, p_sample_loop_learned,
+    ddim_sample_guided,
 )
 from .weights import synth_state_dict  # noqa: F401

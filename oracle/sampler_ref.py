@@ -195,6 +195,37 @@ def interpolate(model: ModelFn, sch: Schedule, x1: Tensor, x2: Tensor, t: Option
     return img
 
 
+def ddim_sample_guided(model: ModelFn, sch: Schedule, x_T: Tensor, S: int, *, eta: float = 0.0, guide: Optional[Tensor] = None,
+                       mask: Optional[Tensor] = None, clip_denoised: bool = True, noises: Optional[Sequence[Tensor]] = None,
+                       guide_noises: Optional[Sequence[Tensor]] = None, objective="pred_noise", self_condition=False,
+                       trace: Optional[list] = None) -> Tensor:
+    """dd:710-777 (without its inline matplotlib display): DDIM where model_predictions is called with
+    clip_x_start=clip_denoised and NO noise re-derivation (dd:728), and after every non-final update the known region is
+    replaced by the guide noised to the *current* step t (dd:746-749: q_sample(guide, time)):
+        img = img * mask + q_sample(guide, t) * (1 - mask)
+    `noises[i]` / `guide_noises[i]` are the draws of loop iteration i.  Always unnormalised at the end (dd:776)."""
+    img = x_T
+    x0 = None
+    for i, (t, tn) in enumerate(ddim_time_pairs(sch.num_timesteps, S)):
+        tb = torch.full((img.shape[0],), t, dtype=torch.long, device=img.device)
+        out = model(img, tb, x0 if self_condition else None)
+        eps, x0 = model_predictions(sch, out, img, t, objective=objective, clip_x_start=clip_denoised)
+        x_t = img
+        if tn < 0:
+            img = x0
+        else:
+            a, an = sch.alphas_cumprod[t], sch.alphas_cumprod[tn]
+            sigma = eta * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
+            c = (1 - an - sigma ** 2).sqrt()
+            z = noises[i] if noises is not None else torch.zeros_like(img)
+            img = x0 * an.sqrt() + c * eps + sigma * z
+            if guide is not None:
+                img = img * mask + q_sample(sch, guide, t, guide_noises[i]) * (1 - mask)
+        if trace is not None:
+            trace.append(dict(t=t, t_next=tn, x_t=x_t, model_out=out, x_start=x0, x_next=img))
+    return (img + 1) * 0.5
+
+
 def ddpm_update_learned(sch: Schedule, model_out: Tensor, x: Tensor, t: int, noise: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
     """One ancestral step of LearnedGaussianDiffusion (learned_gaussian_diffusion.py:91-111 + dd:638-645): the network
     emits 2C channels, (pred_noise | variance interpolation fraction in [-1, 1])."""

@@ -28,12 +28,20 @@ def _worker(rank, world, port, batch, out_dir):
 
     def sampler(local_batch, r):
         lo, hi = bounds[r]
+        if batch < world:           # fewer samples than ranks: every rank draws one row, the first `batch` are kept
+            lo, hi = r, r + 1
         assert hi - lo == local_batch
         rows = torch.arange(lo, hi, dtype=torch.float32)
         return rows[:, None, None, None].expand(-1, 3, 4, 4).contiguous() + 0.5
 
     full = ddm.sample_sharded(sampler, batch)
-    torch.save(full, os.path.join(out_dir, f"rank{rank}.pt"))
+    # the usual torchrun pattern: every rank seeds identically -- the per-call salt (x_T seed + step-noise salt) must differ
+    torch.manual_seed(0)
+    salt_a = ddm.DenoisingDiffusion._call_salt()
+    salt_b = ddm.DenoisingDiffusion._call_salt()
+    torch.manual_seed(0)
+    assert ddm.DenoisingDiffusion._call_salt() == salt_a and salt_a != salt_b      # reproducible after re-seeding
+    torch.save(dict(full=full, salt=salt_a), os.path.join(out_dir, f"rank{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -42,10 +50,14 @@ def test_sample_sharded_two_ranks(tmp_path, batch):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, batch, str(tmp_path)), nprocs=2, join=True)
     want = (torch.arange(batch, dtype=torch.float32) + 0.5)[:, None, None, None].expand(-1, 3, 4, 4)
+    salts = []
     for r in range(2):
-        got = torch.load(os.path.join(tmp_path, f"rank{r}.pt"))
+        rec = torch.load(os.path.join(tmp_path, f"rank{r}.pt"))
+        got = rec["full"]
         assert got.shape == (batch, 3, 4, 4)
         assert torch.equal(got, want)
+        salts.append(rec["salt"])
+    assert salts[0] != salts[1], "ranks seeded identically must still draw different x_T / step noise"
 
 
 def test_shard_bounds_cover_batch():

@@ -301,9 +301,9 @@ def test_row_norm_kernels(lib, C_):
     close(out, R.rmsnorm_act_ref(x.float(), g, ss, 250, 1, res.float()))
 
 
-@pytest.mark.parametrize("n,heads,d", [(1024, 4, 32), (64, 4, 32), (256, 2, 16), (100, 4, 64)])
+@pytest.mark.parametrize("n,heads,d", [(1024, 4, 32), (64, 4, 32), (256, 2, 16), (100, 4, 64), (4096, 4, 32), (16384, 4, 32)])
 def test_linear_attention(lib, n, heads, d):
-    B = 3
+    B = 3 if n <= 1024 else 2          # 4096 / 16384 tokens: the 64-px / 128-px levels of BASELINE configs 3-5
     qkv = dev(rnd((B, n, 3 * heads * d), 120), BF)
     mem = dev(rnd((2, heads, d, 4), 121))
     out = torch.zeros((B, n, heads * d), dtype=BF, device="cuda")

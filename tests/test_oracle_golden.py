@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import (unet_forward, infer_config, synth_state_dict, make_schedule, ddim_time_pairs,
-                    ddim_sample, p_sample_loop, interpolate, p_sample_loop_learned)
+                    ddim_sample, p_sample_loop, interpolate, p_sample_loop_learned, ddim_sample_guided)
 from conftest import GOLDEN
 
 with open(os.path.join(GOLDEN, "manifest.json")) as f:
@@ -26,7 +26,12 @@ UNET_CASES = {
     "unet_text_xattn_32": (8, {}),
     "unet_text_concat_32": (9, {}),
     "unet_full_attn_all_16": (10, {}),
+    # BASELINE shapes (tests/golden/make_golden_r2.py): C3 image-conditional latents, C4 text cross-attention, 128 px
+    "unet_imgcond_64": (7, {}),
+    "unet_text_xattn_64": (8, {}),
+    "unet_base_128": (0, {}),
 }
+MANIFEST_OF = {"unet_imgcond_64": "unet_imgcond_32", "unet_text_xattn_64": "unet_text_xattn_32", "unet_base_128": "unet_base_32"}
 
 
 def _close(a, b, rtol=2e-4):
@@ -39,7 +44,7 @@ def _close(a, b, rtol=2e-4):
 def test_unet_forward_matches_reference(name, golden):
     seed, kw = UNET_CASES[name]
     g = golden(name)
-    sd = synth_state_dict(MANIFEST[name], seed)
+    sd = synth_state_dict(MANIFEST[MANIFEST_OF.get(name, name)], seed)
     cfg = infer_config(sd, **kw)
     extra = {k: g[k] for k in ("x_self_cond", "cond", "text_emb") if k in g}
     with torch.inference_mode():
@@ -140,4 +145,15 @@ def test_ddim_text_cross_attention(golden):
     g = golden("ddim_text_xattn_S3")
     y = ddim_sample(_model("unet_text_xattn_32", 8, text_emb=g["text_emb"]), make_schedule(1000), g["x_T"], 3,
                     unnormalize=False)
+    _close(y, g["y"], 1e-3)
+
+
+@torch.inference_mode()
+def test_ddim_guided(golden):
+    g = golden("ddim_guided_S4")          # dd:710-777 with guide / mask, eta = 0.5
+    y = ddim_sample_guided(_model(), make_schedule(1000), g["x_T"], 4, eta=0.5, guide=g["guide"], mask=g["mask"],
+                           noises=list(g["noises"]), guide_noises=list(g["guide_noises"]))
+    _close(y, g["y"], 1e-3)
+    g = golden("ddim_guided_noguide_S4")  # no guide, clip_denoised=False: raw eps, unclamped x0
+    y = ddim_sample_guided(_model(), make_schedule(1000), g["x_T"], 4, eta=0.5, clip_denoised=False, noises=list(g["noises"]))
     _close(y, g["y"], 1e-3)

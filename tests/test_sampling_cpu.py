@@ -128,3 +128,25 @@ def test_generate_samples_two_ranks(tmp_path):
         assert out[:8].unique().tolist() == [1.0]      # rank 0, first call
         assert out[8:16].unique().tolist() == [1001.0] # rank 1, first call
         assert out[16:].unique().tolist() == [2.0]     # rank 0, second call
+
+
+def test_trainer_adapter_syncs_only_when_weights_change():
+    """attach_fast_sampler (trainer_adapter.py): the EMA copy's sample() is re-pointed at the fast sampler and the weights are
+    mirrored once per change (version counters), not once per call -- dd:1192-1219 calls sample() many times per milestone."""
+    import diffusion_models_b200 as ddm
+    src = ddm.DenoisingDiffusion(ddm.Unet(dim=16, dim_mults=(1, 2)), image_size=16, sampling_timesteps=2)     # stands in for the
+    fast = ddm.DenoisingDiffusion(ddm.Unet(dim=16, dim_mults=(1, 2)), image_size=16, sampling_timesteps=2)    # reference's EMA copy
+    calls = []
+    fast.sample = lambda batch_size=16, return_all_timesteps=False: calls.append(batch_size) or torch.zeros(batch_size, 3, 16, 16)
+    b = ddm.attach_fast_sampler(src, fast)
+    assert src.sample(batch_size=4).shape == (4, 3, 16, 16) and src.sample(batch_size=2).shape == (2, 3, 16, 16)
+    assert calls == [4, 2] and b.syncs == 1
+    w = "model.init_conv.weight"
+    assert torch.equal(fast.state_dict()[w], src.state_dict()[w])
+    with torch.no_grad():
+        for p in src.parameters():
+            p.lerp_(torch.zeros_like(p), 0.5)                     # an EMA-style in-place update
+    src.sample(batch_size=1)
+    assert b.syncs == 2 and torch.equal(fast.state_dict()[w], src.state_dict()[w])
+    src.sample(batch_size=1)
+    assert b.syncs == 2

@@ -53,7 +53,12 @@ CASES = {
     "unet_text_xattn_32": ("text", 8, dict(dim=64, channels=4, text_condition=True, use_cross_attn=True), {}),
     "unet_text_concat_32": ("text", 9, dict(dim=64, channels=4, text_condition=True, use_cross_attn=False), {}),
     "unet_full_attn_all_16": ("base", 10, dict(dim=32, dim_mults=(1, 2), full_attn=(True, True)), {}),
+    # the BASELINE shapes behind the throughput numbers of DESIGN.md section 6 (tests/golden/make_golden_r2.py)
+    "unet_imgcond_64": ("img", 7, dict(dim=64, dim_mults=(1, 2, 4, 8), channels=4, cond_channels=4), {}),
+    "unet_text_xattn_64": ("text", 8, dict(dim=64, channels=4, text_condition=True, use_cross_attn=True), {}),
+    "unet_base_128": ("base", 0, dict(dim=64, dim_mults=(1, 2, 4, 8)), {}),
 }
+MANIFEST_OF = {"unet_imgcond_64": "unet_imgcond_32", "unet_text_xattn_64": "unet_text_xattn_32", "unet_base_128": "unet_base_32"}
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -61,7 +66,7 @@ def test_unet_forward_vs_reference_golden(name, golden):
     kind, seed, kw, _ = CASES[name]
     g = golden(name)
     model, _ = build(kind, seed, **kw)
-    assert {k: list(v.shape) for k, v in model.state_dict().items()} == MANIFEST[name]
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == MANIFEST[MANIFEST_OF.get(name, name)]
     extra = {k: g[k].cuda() for k in ("x_self_cond", "cond", "text_emb") if k in g}
     y = model(g["x"].cuda(), g["t"].cuda(), **extra)
     assert y.shape == g["y"].shape and y.dtype == torch.float32
@@ -93,6 +98,20 @@ def test_state_dict_reload_invalidates_plan():
     with torch.inference_mode():
         ref = unet_forward(sd2, x.cpu(), t.cpu(), infer_config(sd2, heads=2, dim_head=16))
     assert rel_l2(y1, ref) < EPS_TOL and rel_l2(y0, ref) > 0.1
+
+
+def check_trace(trace, sd, cfg, update, **fw):
+    """Teacher forcing on the CUDA trajectory: at every step the oracle network sees the SAME x_t (so the x0 clamp cannot
+    amplify earlier differences) and must agree on the model output within EPS_TOL; the fp32 update applied to the CUDA
+    model output must match the oracle's update bit for bit.  `update(i, st)` -> (x_next, x_start) from the oracle."""
+    for i, st in enumerate(trace):
+        tb = torch.full((st["x_t"].shape[0],), st["t"], dtype=torch.long)
+        with torch.inference_mode():
+            ref_out = unet_forward(sd, st["x_t"].cpu(), tb, cfg, **fw)
+        assert rel_l2(st["model_out"], ref_out) < EPS_TOL, (i, st["t"], rel_l2(st["model_out"], ref_out))
+        want_next, want_x0 = update(i, st)
+        assert torch.equal(st["x_next"].cpu(), want_next), (i, "x_next")
+        assert torch.equal(st["x_start"].cpu(), want_x0), (i, "x_start")
 
 
 def _diffusion(model, **kw):
@@ -150,6 +169,10 @@ def test_ddpm_loop_injected_noise(golden):
     y = d.p_sample_loop((2, 3, 32, 32), noise=g["x_T"].cuda(), step_noise=g["noises"].cuda(), trace=trace)
     assert len(trace) == 6 and trace[0]["t"] == 5
     assert rel_l2(y, g["y"]) < FINAL_TOL and (y.cpu() - g["y"]).abs().mean().item() < 1e-2
+    sch = make_schedule(6, "cosine")
+    _, sd = build("base", 0, dim=64, dim_mults=(1, 2, 4, 8))
+    check_trace(trace, sd, infer_config(sd),
+                lambda i, st: ddpm_update(sch, st["model_out"].cpu(), st["x_t"].cpu(), st["t"], g["noises"][i] if st["t"] > 0 else None))
     y2 = d.sample(batch_size=2, noise=g["x_T"].cuda(), step_noise=g["noises"].cuda())           # graph replay
     assert rel_l2(y2, g["y"]) < FINAL_TOL
 
@@ -175,12 +198,49 @@ def test_learned_variance_vs_reference(golden):
     assert y.shape == (2, 6, 32, 32) and rel_l2(y, g["y"]) < EPS_TOL
     d = ddm.LearnedGaussianDiffusion(model, image_size=32, timesteps=6, beta_schedule="cosine").cuda()
     g = golden("learned_var_T6")
-    y = d.p_sample_loop((2, 3, 32, 32), noise=g["x_T"].cuda(), step_noise=g["noises"].cuda())
+    trace = []
+    y = d.p_sample_loop((2, 3, 32, 32), noise=g["x_T"].cuda(), step_noise=g["noises"].cuda(), trace=trace)
     assert rel_l2(y, g["y"]) < FINAL_TOL and (y.cpu() - g["y"]).abs().mean().item() < 1e-2
+    from oracle import ddpm_update_learned
+    sch = make_schedule(6, "cosine")
+    _, sd = build("base", 12, dim=64, dim_mults=(1, 2, 4, 8), learned_variance=True)
+    check_trace(trace, sd, infer_config(sd), lambda i, st: ddpm_update_learned(
+        sch, st["model_out"].cpu(), st["x_t"].cpu(), st["t"], g["noises"][i] if st["t"] > 0 else None))
     y2 = d.sample(batch_size=2, noise=g["x_T"].cuda(), step_noise=g["noises"].cuda())
     assert rel_l2(y2, g["y"]) < FINAL_TOL
     with pytest.raises(NotImplementedError):
         d.ddim_sample((2, 3, 32, 32))
+
+
+def test_ddim_sample_guided_vs_reference(golden):
+    """ddim_sample_guided (dd:710-777) with a guide + mask at eta = 0.5, and unguided with clip_denoised=False, against the
+    reference run with the same draws; the fp32 update (raw eps, clamp, DDIM step, guide blend) teacher-forced bit-exactly."""
+    from oracle import model_predictions, q_sample
+    model, _ = build("base", 0, dim=64, dim_mults=(1, 2, 4, 8))
+    d = _diffusion(model, sampling_timesteps=4, ddim_sampling_eta=0.5)
+    g = golden("ddim_guided_S4")
+    trace = []
+    y = d.ddim_sample_guided((2, 3, 32, 32), guide=g["guide"].cuda(), mask=g["mask"].cuda(), noise=g["x_T"].cuda(),
+                             step_noise=g["noises"].cuda(), guide_noise=g["guide_noises"].cuda(), trace=trace)
+    assert rel_l2(y, g["y"]) < FINAL_TOL and (y.cpu() - g["y"]).abs().mean().item() < 1e-2
+    sch = make_schedule(1000)
+    for i, (st, (t, tn)) in enumerate(zip(trace, ddim_time_pairs(1000, 4))):
+        out, x_t = st["model_out"].cpu(), st["x_t"].cpu()
+        eps, x0 = model_predictions(sch, out, x_t, t, clip_x_start=True)
+        if tn < 0:
+            want = x0
+        else:
+            a, an = sch.alphas_cumprod[t], sch.alphas_cumprod[tn]
+            sigma = 0.5 * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
+            want = x0 * an.sqrt() + (1 - an - sigma ** 2).sqrt() * eps + sigma * g["noises"][i]
+            want = want * g["mask"] + q_sample(sch, g["guide"], t, g["guide_noises"][i]) * (1 - g["mask"])
+        assert torch.equal(st["x_next"].cpu(), want), i
+        assert torch.equal(st["x_start"].cpu(), x0), i
+    g = golden("ddim_guided_noguide_S4")
+    y = d.ddim_sample_guided((2, 3, 32, 32), clip_denoised=False, noise=g["x_T"].cuda(), step_noise=g["noises"].cuda())
+    assert rel_l2(y, g["y"]) < FINAL_TOL
+    y3 = d.ddim_sample_guided((2, 3, 32, 32), guide=golden("ddim_guided_S4")["guide"].cuda(), mask=golden("ddim_guided_S4")["mask"].cuda())
+    assert torch.isfinite(y3).all()          # in-kernel Philox draws for both noises
 
 
 def test_ddim_pred_v_cosine(golden):
@@ -199,6 +259,13 @@ def test_image_conditional_ddim(golden):
                                            condition_data_folder=None).cuda()
     y = d.ddim_sample((1, 4, 32, 32), sampling_timesteps=3, cond=g["cond"].cuda(), noise=g["x_T"].cuda())
     assert rel_l2(y, g["y"]) < FINAL_TOL
+    trace, sch, pairs = [], make_schedule(1000), ddim_time_pairs(1000, 3)
+    _, sd = build("img", 7, dim=64, dim_mults=(1, 2, 4, 8), channels=4, cond_channels=4)
+    assert torch.equal(d.ddim_sample((1, 4, 32, 32), sampling_timesteps=3, cond=g["cond"].cuda(), noise=g["x_T"].cuda(), trace=trace), y)
+    check_trace(trace, sd, infer_config(sd),
+                lambda i, st: ddim_update(sch, st["model_out"].cpu(), st["x_t"].cpu(), st["t"], pairs[i][1], 0.0, None), cond=g["cond"])
+    with pytest.raises(ValueError):
+        d.interpolate(g["x_T"].cuda(), g["x_T"].cuda(), t=2)           # a conditional model must be given its condition
     # the upstream sample() wrapper runs zero steps under DDIM; ours must actually sample
     d.get_random_condition = lambda batch, device: g["cond"].to(device)
     y2 = d.sample(batch_size=1, noise=g["x_T"].cuda())
@@ -212,6 +279,12 @@ def test_text_cross_attention_ddim(golden):
     d = TextConditionalDenoisingDiffusion(model=model, image_size=32, auto_normalize=False, sampling_timesteps=3).cuda()
     y = d.ddim_sample((1, 4, 32, 32), sampling_timesteps=3, text_emb=g["text_emb"].cuda(), noise=g["x_T"].cuda())
     assert rel_l2(y, g["y"]) < FINAL_TOL
+    trace, sch, pairs = [], make_schedule(1000), ddim_time_pairs(1000, 3)
+    _, sd = build("text", 8, dim=64, channels=4, text_condition=True, use_cross_attn=True)
+    d.ddim_sample((1, 4, 32, 32), sampling_timesteps=3, text_emb=g["text_emb"].cuda(), noise=g["x_T"].cuda(), trace=trace)
+    check_trace(trace, sd, infer_config(sd),
+                lambda i, st: ddim_update(sch, st["model_out"].cpu(), st["x_t"].cpu(), st["t"], pairs[i][1], 0.0, None),
+                text_emb=g["text_emb"])
 
 
 def test_self_condition_loop_and_latent_wrapper():
@@ -259,6 +332,46 @@ def test_large_batch_properties():
     assert torch.isfinite(y).all() and y.min().item() >= 0.0 and y.max().item() <= 1.0
     y_small = d.ddim_sample((16, 3, 32, 32), noise=xT[512:528])
     assert rel_l2(y[512:528], y_small) < 1e-6          # same kernels, same per-row arithmetic
+    # ... and the B = 16 run is tied to ground truth: teacher-forced against the CPU oracle (so B = 1024 is, through the slice)
+    _, sd = build("base", 0, dim=64, dim_mults=(1, 2, 4, 8))
+    trace, sch, pairs = [], make_schedule(1000), ddim_time_pairs(1000, 3)
+    assert torch.equal(d.ddim_sample((16, 3, 32, 32), noise=xT[512:528], trace=trace), y_small)
+    check_trace(trace, sd, infer_config(sd),
+                lambda i, st: ddim_update(sch, st["model_out"].cpu(), st["x_t"].cpu(), st["t"], pairs[i][1], 0.0, None))
+
+
+def test_ldm_image_conditional_encodes_condition_once():
+    """latent_diffusion_image_conditional.py:128 re-encodes the (loop-invariant) condition image on every step; here
+    `cond_vae.encode` must run exactly once per sampling call, and `vae.decode` once, after the loop."""
+    from diffusion_models_b200.latent import ImageConditionalLatentDiffusion
+
+    class CountingVae(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encodes, self.decodes = 0, 0
+
+        def encode(self, img):                       # VQModel.encode returns (quant, emb_loss, info)
+            self.encodes += 1
+            return torch.nn.functional.avg_pool2d(img, 2)[:, :4], None, None
+
+        def decode(self, z):
+            self.decodes += 1
+            return torch.nn.functional.interpolate(z, scale_factor=2.0)[:, :3]
+
+    model, sd = build("img", 7, dim=32, dim_mults=(1, 2), channels=4, cond_channels=4)
+    vae, cvae = CountingVae(), CountingVae()
+    d = ImageConditionalLatentDiffusion(model, vae, (4, 16, 16), cond_vae=cvae, sampling_timesteps=5, condition_data_folder=None).cuda()
+    cond_img = torch.rand((2, 4, 32, 32), generator=torch.Generator().manual_seed(3)).cuda()
+    xT = torch.randn((2, 4, 16, 16), generator=torch.Generator().manual_seed(4)).cuda()
+    y = d.sample(batch_size=2, cond=cond_img, noise=xT)
+    assert y.shape == (2, 3, 32, 32) and (cvae.encodes, cvae.decodes, vae.encodes, vae.decodes) == (1, 0, 0, 1)
+    d2 = ImageConditionalLatentDiffusion(model, vae, (4, 16, 16), cond_vae=cvae, timesteps=7, condition_data_folder=None).cuda()
+    d2.p_sample_loop((2, 4, 16, 16), cond=cond_img, noise=xT)                    # the 1000-step path of the reference, 7 steps here
+    assert cvae.encodes == 2
+    # the result is the plain conditional sampler run on the once-encoded latent
+    z = cvae.encode(cond_img)[0]
+    want = super(ImageConditionalLatentDiffusion, d).ddim_sample((2, 4, 16, 16), cond=z, noise=xT)
+    assert torch.equal(vae.decode(want), y)
 
 
 def test_sampling_script_checkpoint_to_samples(tmp_path):
@@ -285,3 +398,22 @@ def test_sampling_script_checkpoint_to_samples(tmp_path):
     import numpy as np
     pool = np.load(tmp_path / "out" / "fid_samples-3.npz")["images"]
     assert pool.shape == (10, 3, 32, 32) and np.isfinite(pool).all() and pool.min() >= 0.0 and pool.max() <= 1.0
+
+
+def test_trainer_adapter_samples_with_current_ema_weights():
+    """attach_fast_sampler: the (reference-shaped) EMA module's sample() runs on the B200 sampler with ITS weights, and picks up
+    in-place weight updates -- what dd:1192-1219 needs between milestones."""
+    import diffusion_models_b200 as ddm
+    src_model, _ = build("base", 0, dim=64, dim_mults=(1, 2, 4, 8))
+    src = _diffusion(src_model, sampling_timesteps=3)                  # stands in for Trainer.ema.ema_model
+    fast = ddm.DenoisingDiffusion(ddm.Unet(dim=64, dim_mults=(1, 2, 4, 8)), image_size=32, sampling_timesteps=3).cuda()
+    binding = ddm.attach_fast_sampler(src, fast)
+    xT = torch.randn((4, 3, 32, 32), generator=torch.Generator().manual_seed(21)).cuda()
+    want = ddm.DenoisingDiffusion.ddim_sample(src, (4, 3, 32, 32), noise=xT)       # the source's own (unpatched) sampler
+    assert torch.equal(src.ddim_sample((4, 3, 32, 32), noise=xT), want) and binding.syncs == 1
+    with torch.no_grad():
+        for p in src.parameters():
+            p.mul_(0.9)
+    want2 = ddm.DenoisingDiffusion.ddim_sample(src, (4, 3, 32, 32), noise=xT)
+    got2 = src.ddim_sample((4, 3, 32, 32), noise=xT)
+    assert binding.syncs == 2 and torch.equal(got2, want2) and not torch.equal(got2, want)
