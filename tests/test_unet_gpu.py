@@ -100,7 +100,7 @@ def test_state_dict_reload_invalidates_plan():
     assert rel_l2(y1, ref) < EPS_TOL and rel_l2(y0, ref) > 0.1
 
 
-def check_trace(trace, sd, cfg, update, **fw):
+def check_trace(trace, sd, cfg, update, exact=True, **fw):
     """Teacher forcing on the CUDA trajectory: at every step the oracle network sees the SAME x_t (so the x0 clamp cannot
     amplify earlier differences) and must agree on the model output within EPS_TOL; the fp32 update applied to the CUDA
     model output must match the oracle's update bit for bit.  `update(i, st)` -> (x_next, x_start) from the oracle."""
@@ -110,7 +110,10 @@ def check_trace(trace, sd, cfg, update, **fw):
             ref_out = unet_forward(sd, st["x_t"].cpu(), tb, cfg, **fw)
         assert rel_l2(st["model_out"], ref_out) < EPS_TOL, (i, st["t"], rel_l2(st["model_out"], ref_out))
         want_next, want_x0 = update(i, st)
-        assert torch.equal(st["x_next"].cpu(), want_next), (i, "x_next")
+        if exact:
+            assert torch.equal(st["x_next"].cpu(), want_next), (i, "x_next")
+        else:           # an update with a transcendental (exp of the learned log-variance): a few ulp between libdevice and ATen
+            assert (st["x_next"].cpu() - want_next).abs().max().item() <= 1e-5 * max(1.0, want_next.abs().max().item()), (i, "x_next")
         assert torch.equal(st["x_start"].cpu(), want_x0), (i, "x_start")
 
 
@@ -205,7 +208,7 @@ def test_learned_variance_vs_reference(golden):
     sch = make_schedule(6, "cosine")
     _, sd = build("base", 12, dim=64, dim_mults=(1, 2, 4, 8), learned_variance=True)
     check_trace(trace, sd, infer_config(sd), lambda i, st: ddpm_update_learned(
-        sch, st["model_out"].cpu(), st["x_t"].cpu(), st["t"], g["noises"][i] if st["t"] > 0 else None))
+        sch, st["model_out"].cpu(), st["x_t"].cpu(), st["t"], g["noises"][i] if st["t"] > 0 else None), exact=False)
     y2 = d.sample(batch_size=2, noise=g["x_T"].cuda(), step_noise=g["noises"].cuda())
     assert rel_l2(y2, g["y"]) < FINAL_TOL
     with pytest.raises(NotImplementedError):
