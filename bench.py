@@ -117,25 +117,85 @@ def time_cpu_reference(batch, iters, warm=1):
     return times
 
 
+def cpu_ddim100(batch):
+    """One complete DDIM-100 sampling call of the reference algorithm (oracle port) on the host cores; returns seconds."""
+    from oracle import make_schedule, ddim_sample
+    torch.set_num_threads(os.cpu_count())
+    model, sch = oracle_model(), make_schedule(1000)
+    x = torch.randn((batch, CHANNELS, IMAGE, IMAGE), generator=torch.Generator().manual_seed(1234))
+    t0 = time.perf_counter()
+    with torch.inference_mode():
+        ddim_sample(model, sch, x, DDIM_STEPS)
+    return time.perf_counter() - t0
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path (the oracle port: the reference is Python and cannot travel to the GPU
+    box), on all host cores.  One step = ONE COMPLETE DDIM-100 sampling call, timed as such (no
+    extrapolation); the batch is the bounded sample: small enough that `--steps K --warmup W` calls end within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 16
-    per_step_iters = 2                       # a bounded sample of the 100-iteration workload per "step"
-    all_t = time_cpu_reference(batch, per_step_iters * (args.steps + args.warmup), warm=0)
-    timed = all_t[per_step_iters * args.warmup:]
-    it = statistics.median(timed)
-    value = batch / (DDIM_STEPS * it)
-    sample = (f"B={batch}, {len(timed)} timed loop iterations (U-Net fp32 + DDIM update) of the 100 per image after "
-              f"{per_step_iters * args.warmup} warm-up; images/s = B / (100 x median iteration time)")
+    batch = int(os.environ.get("DDM_REF_BATCH", "0"))
+    if batch <= 0:       # calibrate: the largest batch of {1, 2, 4} whose DDIM-100 call stays under ~8 s on this host
+        it = statistics.median(time_cpu_reference(4, 2, warm=1))
+        batch = 4 if it * DDIM_STEPS <= 8.0 else (2 if it * DDIM_STEPS <= 14.0 else 1)
+    for _ in range(args.warmup):
+        cpu_ddim100(batch)
+    times = [cpu_ddim100(batch) for _ in range(args.steps)]
+    total = sum(times)
+    value = batch * args.steps / total
+    sample = (f"B={batch} per call, {args.steps} complete DDIM-100 sampling calls (100 fp32 U-Net evaluations + DDIM updates each) timed "
+              f"after {args.warmup} warm-up calls; images/s = B x calls / total time (the CPU's best rate, at B=16, is in the GPU "
+              f"arm's cpu_baseline)")
     line = {"impl": "reference", "metric": "ddim100_images_per_sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": it * DDIM_STEPS * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": batch, "ddim_steps": DDIM_STEPS, "device": "host CPU"},
+            "config": {"workload": WORKLOAD, "per_gpu_batch": batch, "global_batch": batch, "ddim_steps": DDIM_STEPS,
+                       "device": "host CPU", "weights": "synthetic seed 0"},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def time_gpu_stock_pytorch(dev, batch, iters=4, warm=2):
+    """Second comparator: the same algorithm (oracle port) through stock PyTorch
+    on this B200 -- cuDNN / cuBLAS library kernels -- in fp32 with TF32 off (the reference's sampling precision) and under
+    bf16 autocast.  Bounded: `iters` loop iterations (U-Net + DDIM update) each, extrapolated to the 100 of a sampling call."""
+    from oracle import unet_forward, infer_config, synth_state_dict, make_schedule, ddim_time_pairs, ddim_update
+    import diffusion_models_b200 as ddm
+    shapes = {k: tuple(s) for k, (s, _) in ddm.Unet(**MODEL_KW).spec.params.items()}
+    sd = {k: v.to(dev) for k, v in synth_state_dict(shapes, 0).items()}
+    cfg, sch = infer_config(sd), make_schedule(1000)
+    sch = type(sch)(**{f: getattr(sch, f).to(dev) for f in sch.__dataclass_fields__})
+    pairs = ddim_time_pairs(1000, DDIM_STEPS)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    out = {}
+    try:
+        for name, autocast in (("fp32_tf32_off", False), ("bf16_autocast", True)):
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.benchmark = True
+            x = torch.randn((batch, CHANNELS, IMAGE, IMAGE), generator=torch.Generator().manual_seed(1234)).to(dev)
+            ts = []
+            with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                for i in range(warm + iters):
+                    t, tn = pairs[i]
+                    torch.cuda.synchronize(dev)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    eps = unet_forward(sd, x, torch.full((batch,), t, dtype=torch.long, device=dev), cfg).float()
+                    x, _ = ddim_update(sch, eps, x, t, tn, 0.0, None)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                    if i >= warm:
+                        ts.append(e0.elapsed_time(e1) * 1e-3)
+            out[name] = batch / (DDIM_STEPS * statistics.median(ts))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    return {"unit": "images/s", "fp32_tf32_off": out["fp32_tf32_off"], "bf16_autocast": out["bf16_autocast"], "kind": "port",
+            "sample": f"oracle port on cuda through stock PyTorch {torch.__version__} (cuDNN/cuBLAS), B={batch}, {iters} timed loop "
+                      f"iterations after {warm} warm-up per precision; images/s = B / (100 x median iteration time)"}
 
 
 def run_ours(args):
@@ -152,6 +212,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    scaling = "weak"
+    if args.global_batch:                                   # strong scaling: the global batch is fixed, split over the ranks
+        assert args.global_batch % world == 0, "--global-batch must divide by the number of GPUs"
+        B, scaling = args.global_batch // world, "strong"
     shape = (B, CHANNELS, IMAGE, IMAGE)
 
     model = ddm.Unet(**MODEL_KW)
@@ -161,7 +225,7 @@ def run_ours(args):
 
     gen = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(shape, generator=gen).pin_memory()
-    y_host = torch.empty((B * world,) + shape[1:]).pin_memory()
+    y_host = torch.empty(shape).pin_memory()                 # every rank reads back its own shard of the gathered result
     x_dev = x_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
@@ -171,7 +235,7 @@ def run_ours(args):
     def sample_e2e():
         xd = x_host.to(dev, non_blocking=True)
         out = ddm.sample_sharded(lambda b, r: diff.ddim_sample(shape, noise=xd), B * world)
-        y_host.copy_(out, non_blocking=True)
+        y_host.copy_(out[rank * B:(rank + 1) * B], non_blocking=True)
         return out
 
     def timed(fn, steps):
@@ -211,13 +275,13 @@ def run_ours(args):
     pk, pk_src = peaks()
 
     line = {"metric": "ddim100_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "ddim_steps": DDIM_STEPS,
                        "parallelism": f"batch-sharded x{world}, one final all-gather", "weights": "synthetic seed 0",
                        "l2": "256 MiB flush write between timed iterations; per-step working set >> 126 MB L2"},
-            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": y_host.numel() * 4},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
+                    "d2h_bytes_per_step": y_host.numel() * 4 * world},
             "gpu_launches": int(gpu_launches), "clocks": clocks.summary()}
 
     if rank == 0:
@@ -225,28 +289,43 @@ def run_ours(args):
         # non-conv kernels count against it), plus the dominant layer shape timed alone.
         ach = value / world * flops_img / 1e12
         dom = time_dominant_conv(model, B, dev)
+        traffic, traffic_src = dominant_traffic(B)
         line["roofline"] = {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                            "frac": dom["tflops"] / pk["bf16_tflops"], "traffic": DOMINANT_DRAM_BYTES if B == 1024 else None,
-                            "traffic_source": "dram__bytes_read+write of this launch in profiles/r01_ncu_full_conv_v10.txt (ncu --set full, B=1024)",
+                            "frac": dom["tflops"] / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
                             "algorithmic_bytes": 2 * B * IMAGE * IMAGE * 64 * 2, "peak_source": pk_src + " (burst, kernel timed alone)",
                             "kernel": "conv_tc_kernel", "layer": dom["layer"], "us_per_launch": dom["us"],
                             "whole_step": {"achieved": ach, "peak": pk["bf16_tflops_sustained"], "frac": ach / pk["bf16_tflops_sustained"],
                                            "unit": "TFLOP/s", "gflop_per_image": flops_img / 1e9,
                                            "note": "conv+linear algorithmic FLOPs / full sampling time, per GPU; peak = sustained"}}
         if world == 1:
-            it = time_cpu_reference(16, 4, warm=1)
+            it = time_cpu_reference(16, 30, warm=2)
             med = statistics.median(it)
             line["cpu_baseline"] = {"value": 16 / (DDIM_STEPS * med), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "oracle port, B=16, 4 timed loop iterations after 1 warm-up; images/s = 16 / (100 x median)"}
+                                    "sample": "oracle port (reference algorithm, fp32, all host cores), B=16, 30 timed loop iterations "
+                                              "(U-Net + DDIM update) after 2 warm-up; images/s = 16 / (100 x median iteration time)"}
+            if not os.environ.get("DDM_BENCH_NO_GPU_BASELINE"):
+                del diff, model
+                torch.cuda.empty_cache()
+                line["gpu_baseline"] = time_gpu_stock_pytorch(dev, min(B, 1024))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-# ncu --set full capture of downs.0.0.block1 at B=1024 (profiles/r01_ncu_full_conv_v10.txt): 134.37 MB read + 90.12 MB written
-# (the tail of the 134 MB output is still in L2 when the kernel ends)
-DOMINANT_DRAM_BYTES = 134366208 + 90123264
+def dominant_traffic(B):
+    """DRAM bytes of the dominant launch, from the `ncu --set full` capture of the CURRENT kernels that scripts/ncu_traffic.py
+    distilled into profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch).  null when the capture
+    is missing or was taken at another batch."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            rec = json.load(f)["downs.0.0.block1"]
+        if rec.get("batch") != B:
+            return None, f"profiles/traffic.json holds B={rec.get('batch')}, this run is B={B}"
+        return int(rec["dram_read"] + rec["dram_write"]), rec["source"]
+    except Exception:
+        return None, "no ncu capture of the current build in profiles/traffic.json"
 
 
 def time_dominant_conv(model, B, dev, reps=20):
@@ -275,7 +354,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("DDM_BENCH_BATCH", "1024")), help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("DDM_BENCH_BATCH", "1024")), help="per-GPU batch (weak scaling)")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fixed global batch split over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,9 +39,17 @@ constexpr int kCtxN = 144;       // context accumulator columns (128 + the ones 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kThreads = kEpiThreads + 32;     // + the control warp
-// named barriers: 0 = __syncthreads, 1 = epilogue warps only, the rest = epilogue -> control hand-overs
-constexpr int kBarEpi = 1, kBarEdone = 2, kBarYdone = 4, kBarCdone = 6, kBarMtdone = 7;
+constexpr int kThreads = kEpiThreads + 96;     // + the three control warps (TMA, K issuer, Cx issuer)
+constexpr int kGroupThreads = kEpiThreads / 2; // two epilogue groups of 8 warps
+// named barriers: 0 = __syncthreads, 1 / 2 = the two epilogue groups, 8 = all epilogue warps, the rest = epilogue -> control
+// (edone -> both issuers, release / ydone -> the TMA warp, cdone -> Cx, mtdone -> both issuers)
+// Over-run safety (a bar.arrive for the next use of an id before the consumer passed the current one is undefined):
+//   edone : the group's next arrival needs an MMA that K issues after passing this one, and the barrier only completes once Cx
+//           (and in pass 1 the TMA warp) arrived too -> two ids (buffer parity) suffice;
+//   ydone : consumed by the TMA warp alone; with a ring of kNbuf = 4 tiles, tile t + 4 can only be loaded after the TMA warp
+//           stored tile t, i.e. passed ydone(t) -> four ids (t & 3) can never be over-run.
+constexpr int kBarEpi = 1, kBarEdone = 3, kBarYdone = 5, kBarCdone = 9, kBarMtdone = 10, kBarAll = 11;
+constexpr int kPass1Edone = kGroupThreads + 96, kPass2Edone = kGroupThreads + 64;    // group + (K, Cx, TMA) / + (K, Cx)
 
 struct LaParams {
     const float* bias_out;   // [C]
@@ -56,7 +64,7 @@ constexpr int kLafTraceCap = 4096;
 __device__ long long g_laf_trace[2 * kLafTraceCap * 2];      // [role: 0 control, 1 epilogue warp 0][event][tag, clock]
 
 struct alignas(8) LaBars {
-    uint64_t xfull[4];
+    uint64_t xfull[8];
     uint64_t accfull[2];     // pass 1: [K^T|V^T] chunk ready; pass 2: Q tile ready
     uint64_t pvdone[2];      // pass 1: context MMA finished reading P/V buffer
     uint64_t yfull[2];       // pass 2: Y tile ready
@@ -88,8 +96,8 @@ struct LaSmem {
     static constexpr int off_g = off_bias + C * 4;                    // [C]
     static constexpr int off_pm = off_g + C * 4;                      // [128][4] exp(mem_k - shift)
     static constexpr int off_mv = off_pm + 128 * 16;                  // [128][4] mem_v
-    static constexpr int off_red = off_mv + 128 * 16;                 // [2 tiles][4 parts][128]
-    static constexpr int off_bars = off_red + 2 * 4 * 128 * 4;
+    static constexpr int off_red = off_mv + 128 * 16;                 // [2 groups][2 halves][128]
+    static constexpr int off_bars = off_red + 2 * 2 * 128 * 4;
     static constexpr int kTotal = off_bars + static_cast<int>(sizeof(LaBars));
     static_assert(kTotal + 1024 <= 227 * 1024, "shared-memory plan does not fit");
     static_assert(kUBytes >= 65536, "union region must hold two Qs buffers");
@@ -139,7 +147,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int total_tiles = n_img * 2 * T;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&bars->xfull[i], 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&bars->xfull[i], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->accfull[i], 1); mbar_init(&bars->pvdone[i], 1); mbar_init(&bars->yfull[i], 1); }
         mbar_init(&bars->wfull, 1);
         mbar_init(&bars->woutfull, 1);
@@ -171,7 +179,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float mcl = __ldg(p.k_shift + (row & 127)) * kLog2e;       // pass 1: this thread's channel
 
-    const bool tr_on = p.trace != 0 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kEpiWarps);
+    const bool tr_on = p.trace != 0 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kEpiWarps + 1);
     int tr_n = 0;
     auto TR = [&](int ev, int idx) {
         if (tr_on && tr_n < kLafTraceCap) {
@@ -188,241 +196,246 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint64_t desc0 = umma_desc_sw128(0);
     auto desc = [&](uint32_t addr) -> uint64_t { return desc0 | static_cast<uint64_t>((addr & 0x3FFFF) >> 4); };
 
-    if (warp == kEpiWarps) {
-        // =============================================================================================== control warp
-        // Issues every TMA load / store and every MMA; never touches data.  It learns that the epilogue warps finished
-        // a step through the *done mbarriers (one arrival per epilogue warp) and tells them through the TMA / commit
-        // mbarriers, so the epilogue warps never wait for this warp's instruction issue, only for real completions.
+    if (warp >= kEpiWarps) {
+        // =============================================================================================== control warps
+        // Three single-purpose warps that never touch data:
+        //   T  (warp 16): every TMA load and store -- W_qkv once, W_out per image, the x-tile ring, the y tiles;
+        //   K  (warp 17): the MMAs that FILL the per-group accumulators: [K^T|V^T] chunks (pass 1), Q tiles (pass 2);
+        //   Cx (warp 18): the MMAs that CONSUME a finished epilogue: context (pass 1), M (between), Y (pass 2).
+        // A tcgen05.mma blocks its issuing thread while the ~4-deep MMA queue is full, i.e. for about the execution time of the
+        // batch (8 x 48 cycles for a chunk): one issuer for everything was the critical path (1.9 k cycles per chunk for 0.7 k of
+        // tensor work).  They hear from the epilogue groups through named barriers (bar.arrive by the group, bar.sync here:
+        // every mbarrier poller slows the CTA's mbarrier traffic, a wait on a completed phase took ~700 cycles with 17 pollers)
+        // and talk back through the TMA / tcgen05.commit mbarriers.  Barrier ids alternate with the buffer because a group may
+        // arrive for step i + 2 only after an MMA that is issued behind step i's bar.sync.
         const uint32_t idesc_kv = umma_idesc_bf16(128, kChunkTok);
         const uint32_t idesc_ctx = umma_idesc_bf16(128, kCtxN);
         const uint32_t idesc_128 = umma_idesc_bf16(128, 128);
         const uint32_t idesc_y = umma_idesc_bf16(128, C);
-        // x-tile stream: global tile index g = image_iter * 2T + pass * T + t lives in buffer g % NB
-        int next_load = 0, released = 0;
-        auto pump = [&]() {
-            while (next_load < total_tiles && next_load < released + NB) {
-                const int g = next_load++;
-                if (elect_one()) {
-                    const int it = g / (2 * T);
-                    const int s = g - it * 2 * T;
-                    const int t = s >= T ? s - T : s;
-                    const int b = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-                    const int slot = g % NB;
-                    mbar_arrive_expect_tx(&bars->xfull[slot], static_cast<uint32_t>(L::kXTile));
-                    for (int a = 0; a < kAtoms; ++a)
-                        tma_load_2d(smem + L::off_x + slot * L::kXTile + a * (kTileTok * 128), &tmX, &bars->xfull[slot], a * 64,
-                                    b * p.n + t * kTileTok);
-                }
-                __syncwarp();
-            }
-        };
         auto wait_x = [&](int g) { wait_leader(&bars->xfull[g % NB], static_cast<uint32_t>(g / NB) & 1u); };
-        auto issue_kv = [&](int g_tile, int j) {          // chunk j of the image -> accumulator buffer j & 1
-            if (elect_one()) {
-                const uint32_t xb = sb + L::off_x + (g_tile % NB) * L::kXTile + (j & 1) * (kChunkTok * 128);
-                const uint32_t d0 = tmem_base + static_cast<uint32_t>((j & 1) * 128);
-#pragma unroll
-                for (int kind = 0; kind < 2; ++kind) {
-#pragma unroll
-                    for (int a = 0; a < kAtoms; ++a) {
-                        const uint64_t ad = desc(sb + L::off_w + a * (384 * 128) + (1 + kind) * (128 * 128));
-                        const uint64_t bd = desc(xb + a * (kTileTok * 128));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(d0 + kind * 64, ad + 2u * k, bd + 2u * k, idesc_kv, (a | k) ? 1u : 0u);
-                    }
-                }
-                umma_commit(&bars->accfull[j & 1]);
-            }
-            __syncwarp();
-        };
-        auto issue_ctx = [&](int j) {
-            if (elect_one()) {
-                const uint64_t ad = desc(sb + L::off_u + (j & 1) * L::kPBytes);
-                const uint64_t bd = desc(sb + L::off_u + 2 * L::kPBytes + (j & 1) * L::kVBytes);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256u, ad + 2u * k, bd + 2u * k, idesc_ctx, (j | k) ? 1u : 0u);
-                umma_commit(&bars->pvdone[j & 1]);
-            }
-            __syncwarp();
-        };
-        auto issue_q = [&](int g_tile, int t) {
-            if (elect_one()) {
-                const uint32_t xb = sb + L::off_x + (g_tile % NB) * L::kXTile;
-#pragma unroll
-                for (int a = 0; a < kAtoms; ++a) {
-                    const uint64_t ad = desc(xb + a * (kTileTok * 128));
-                    const uint64_t bd = desc(sb + L::off_w + a * (384 * 128));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_128, (a | k) ? 1u : 0u);
-                }
-                umma_commit(&bars->accfull[t & 1]);
-            }
-            __syncwarp();
-        };
-        auto issue_y = [&](int t) {
-            if (elect_one()) {
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const uint64_t ad = desc(sb + L::off_u + (t & 1) * 32768 + a * 16384);
-                    const uint64_t bd = desc(sb + L::off_mt + a * (C * 128));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + 256u + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_y, (a | k) ? 1u : 0u);
-                }
-                umma_commit(&bars->yfull[t & 1]);
-            }
-            __syncwarp();
-        };
-        // Epilogue -> control hand-overs are named barriers (the 512 epilogue threads bar.arrive, this warp bar.syncs):
-        // every mbarrier poller slows the CTA's other mbarrier traffic, and with 16 + 1 polling warps a wait on an already
-        // completed phase took ~700 cycles.  Two ids per event, alternating with the buffer, because the epilogue warps may
-        // arrive for step i + 1 before this warp has consumed step i (never for i + 2: that needs an MMA issued after it).
-        uint32_t ph_misc = 0;
-        auto wait_edone = [&](int i) { named_bar_sync(kBarEdone + i, kThreads); tc_fence_after(); };
-        auto wait_ydone = [&](int i) { named_bar_sync(kBarYdone + i, kThreads); tc_fence_after(); };
+        auto wait_edone = [&](int i, int count) { named_bar_sync(kBarEdone + i, count); tc_fence_after(); };
 
-        // W_out [C][128] is loaded into the M^T region for every image (16 KB from L2, issued as soon as the previous image's
-        // last Y MMA has read M^T): the M GEMM reads it before the epilogue warps overwrite the region with M^T
-        auto load_wout = [&]() {
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&bars->woutfull, static_cast<uint32_t>(L::kMtBytes));
-                for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_mt + a * (C * 128), &tmWout, &bars->woutfull, a * 64, 0);
-            }
-            __syncwarp();
-        };
-        if (elect_one()) {     // W_qkv (pre-norm gain folded in) stays resident
-            mbar_arrive_expect_tx(&bars->wfull, static_cast<uint32_t>(L::kWBytes));
-            for (int a = 0; a < kAtoms; ++a)
-                for (int rb = 0; rb < 3; ++rb)
-                    tma_load_2d(smem + L::off_w + a * (384 * 128) + rb * (128 * 128), &tmWqkv, &bars->wfull, a * 64, rb * 128);
-        }
-        __syncwarp();
-        load_wout();
-        pump();
-        wait_leader(&bars->wfull, 0u);
-
-        int G = 0;
-        int stores_in_flight = 0;      // bulk groups committed and not yet waited for
-        for (int it = 0; it < n_img; ++it, G += 2 * T) {
-            const int b = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-            // ---- pass 1
-            wait_x(G);
-            tc_fence_after();
-            issue_kv(G, 0);
-            TR(10, 0);
-            for (int j = 0; j < J; ++j) {
-                if (j + 1 < J) {
-                    const int gt = G + ((j + 1) >> 1);
-                    if (((j + 1) & 1) == 0) wait_x(gt);
-                    TR(9, j + 1);
-                    issue_kv(gt, j + 1);        // its accumulator was released by epilogue j - 1 (edone waited below)
-                    TR(10, j + 1);
-                }
-                wait_edone(j & 1);              // P/V of chunk j written, accumulator j & 1 read out
-                TR(11, j);
-                issue_ctx(j);
-                TR(12, j);
-                if (j & 1) {                    // both chunks of tile j >> 1 multiplied (epilogue j saw accfull) and its norms taken
-                    if (stores_in_flight) { if (elect_one()) bulk_wait_group_read<0>(); __syncwarp(); stores_in_flight = 0; }
-                    released = G + (j >> 1) + 1;
-                    pump();
-                }
-            }
-            // ---- between the passes: M[(h,d)][c] = ctx[(h,d)][(h',e)] . W_out[c][(h',e)]^T   (W_out sits in the M^T region)
-            named_bar_sync(kBarCdone, kThreads);              // block-diagonal context written (every context MMA retired)
-            TR(30, it);
-            wait_leader(&bars->woutfull, ph_misc & 1u);
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const uint64_t ad = desc(sb + L::off_u + a * 16384);
-                    const uint64_t bd = desc(sb + L::off_mt + a * (C * 128));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc_y, (a | k) ? 1u : 0u);
-                }
-                umma_commit(&bars->mdone);
-            }
-            __syncwarp();
-            TR(31, it);
-            named_bar_sync(kBarMtdone, kThreads);             // M^T written, its accumulator read out
-            TR(32, it);
-            ph_misc ^= 1u;
-            tc_fence_after();
-            // ---- pass 2
-            const int G2 = G + T;
-            wait_x(G2);
-            issue_q(G2, 0);
-            for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) {
-                    wait_x(G2 + t + 1);
-                    issue_q(G2 + t + 1, t + 1);     // its accumulator was released by epilogue Q t - 1
-                }
-                TR(20, t);
-                wait_edone(t & 1);                  // softmax(q) tile written
-                TR(21, t);
-                issue_y(t);                         // its accumulator was released by epilogue Y t - 2 (ydone waited below)
-                TR(22, t);
-                if (t >= 1) {
-                    wait_ydone((t - 1) & 1);
-                    TR(23, t - 1);
+        if (warp == kEpiWarps) {
+            // ------------------------------------------------------------------------------------------- T: TMA
+            // x-tile stream: global tile index g = image_iter * 2T + pass * T + t lives in buffer g % NB
+            int next_load = 0, released = 0;
+            auto pump = [&]() {
+                while (next_load < total_tiles && next_load < released + NB) {
+                    const int g = next_load++;
                     if (elect_one()) {
-                        // the previous store has read its tile by now: hand that buffer back to the loader first
-                        if (stores_in_flight) bulk_wait_group_read<0>();
+                        const int it = g / (2 * T);
+                        const int s = g - it * 2 * T;
+                        const int t = s >= T ? s - T : s;
+                        const int b = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+                        const int slot = g % NB;
+                        mbar_arrive_expect_tx(&bars->xfull[slot], static_cast<uint32_t>(L::kXTile));
                         for (int a = 0; a < kAtoms; ++a)
-                            tma_store_2d(&tmY, smem + L::off_x + ((G2 + t - 1) % NB) * L::kXTile + a * (kTileTok * 128), a * 64,
-                                         b * p.n + (t - 1) * kTileTok);
-                        bulk_commit_group();
+                            tma_load_2d(smem + L::off_x + slot * L::kXTile + a * (kTileTok * 128), &tmX, &bars->xfull[slot], a * 64,
+                                        b * p.n + t * kTileTok);
                     }
                     __syncwarp();
-                    if (stores_in_flight) { released = G2 + t - 1; pump(); }
-                    stores_in_flight = 1;
                 }
-            }
-            wait_ydone((T - 1) & 1);
-            if (elect_one()) {
-                if (stores_in_flight) bulk_wait_group_read<0>();
+            };
+            // W_out [C][128] goes into the M^T region for every image (16 KB from L2, as soon as the previous image's last Y MMA
+            // has read M^T): the M GEMM reads it before the epilogue warps overwrite the region with M^T
+            auto load_wout = [&]() {
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bars->woutfull, static_cast<uint32_t>(L::kMtBytes));
+                    for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_mt + a * (C * 128), &tmWout, &bars->woutfull, a * 64, 0);
+                }
+                __syncwarp();
+            };
+            if (elect_one()) {     // W_qkv (pre-norm gain folded in) stays resident
+                mbar_arrive_expect_tx(&bars->wfull, static_cast<uint32_t>(L::kWBytes));
                 for (int a = 0; a < kAtoms; ++a)
-                    tma_store_2d(&tmY, smem + L::off_x + ((G2 + T - 1) % NB) * L::kXTile + a * (kTileTok * 128), a * 64,
-                                 b * p.n + (T - 1) * kTileTok);
-                bulk_commit_group();
+                    for (int rb = 0; rb < 3; ++rb)
+                        tma_load_2d(smem + L::off_w + a * (384 * 128) + rb * (128 * 128), &tmWqkv, &bars->wfull, a * 64, rb * 128);
             }
             __syncwarp();
-            if (stores_in_flight) { released = G2 + T - 1; pump(); }
-            stores_in_flight = 1;
-            if (it + 1 < n_img) load_wout();
+            load_wout();
+            pump();
+            int G = 0;
+            for (int it = 0; it < n_img; ++it, G += 2 * T) {
+                const int b = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+                for (int j = 0; j < J; ++j) {       // pass 1: a tile is free once both of its chunks went through their epilogues
+                    named_bar_sync(kBarEdone + (j & 1), kPass1Edone);
+                    if (j & 1) { released = G + (j >> 1) + 1; pump(); }
+                }
+                const int G2 = G + T;
+                for (int t = 0; t < T; ++t) {       // pass 2: y tile (written in place over its x tile) -> global
+                    named_bar_sync(kBarYdone + (t & 3), kGroupThreads + 32);
+                    if (elect_one()) {
+                        for (int a = 0; a < kAtoms; ++a)
+                            tma_store_2d(&tmY, smem + L::off_x + ((G2 + t) % NB) * L::kXTile + a * (kTileTok * 128), a * 64, b * p.n + t * kTileTok);
+                        bulk_commit_group();
+                        bulk_wait_group_read<0>();      // the buffer goes back to the loader as soon as the store has read it
+                    }
+                    __syncwarp();
+                    released = G2 + t + 1;
+                    pump();
+                }
+                if (it + 1 < n_img) load_wout();    // every Y MMA of this image has retired (its epilogue ran)
+            }
+            if (elect_one()) bulk_wait_group<0>();
+            __syncwarp();
+        } else if (warp == kEpiWarps + 1) {
+            // ------------------------------------------------------------------------------------------- K: accumulator-filling MMAs
+            auto issue_kv = [&](int g_tile, int j) {          // chunk j of the image -> accumulator buffer j & 1
+                if (elect_one()) {
+                    const uint32_t xb = sb + L::off_x + (g_tile % NB) * L::kXTile + (j & 1) * (kChunkTok * 128);
+                    const uint32_t d0 = tmem_base + static_cast<uint32_t>((j & 1) * 128);
+#pragma unroll
+                    for (int kind = 0; kind < 2; ++kind) {
+#pragma unroll
+                        for (int a = 0; a < kAtoms; ++a) {
+                            const uint64_t ad = desc(sb + L::off_w + a * (384 * 128) + (1 + kind) * (128 * 128));
+                            const uint64_t bd = desc(xb + a * (kTileTok * 128));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d0 + kind * 64, ad + 2u * k, bd + 2u * k, idesc_kv, (a | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&bars->accfull[j & 1]);
+                }
+                __syncwarp();
+            };
+            auto issue_q = [&](int g_tile, int t) {
+                if (elect_one()) {
+                    const uint32_t xb = sb + L::off_x + (g_tile % NB) * L::kXTile;
+#pragma unroll
+                    for (int a = 0; a < kAtoms; ++a) {
+                        const uint64_t ad = desc(xb + a * (kTileTok * 128));
+                        const uint64_t bd = desc(sb + L::off_w + a * (384 * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_128, (a | k) ? 1u : 0u);
+                    }
+                    umma_commit(&bars->accfull[t & 1]);
+                }
+                __syncwarp();
+            };
+            wait_leader(&bars->wfull, 0u);
+            int G = 0;
+            for (int it = 0; it < n_img; ++it, G += 2 * T) {
+                wait_x(G);
+                tc_fence_after();
+                issue_kv(G, 0);
+                TR(10, 0);
+                issue_kv(G, 1);
+                for (int j = 0; j < J; ++j) {
+                    wait_edone(j & 1, kPass1Edone);              // accumulator j & 1 read out by its group
+                    TR(11, j);
+                    if (j + 2 < J) {
+                        const int gt = G + ((j + 2) >> 1);
+                        if ((j & 1) == 0) wait_x(gt);
+                        issue_kv(gt, j + 2);
+                        TR(10, j + 2);
+                    }
+                }
+                named_bar_sync(kBarMtdone, kEpiThreads + 64);      // M^T written: accumulator columns 0..63 are free again
+                tc_fence_after();
+                const int G2 = G + T;
+                wait_x(G2);
+                issue_q(G2, 0);
+                if (T > 1) { wait_x(G2 + 1); issue_q(G2 + 1, 1); }
+                for (int t = 0; t < T; ++t) {
+                    wait_edone(t & 1, kPass2Edone);              // Q accumulator t & 1 read out
+                    TR(21, t);
+                    if (t + 2 < T) { wait_x(G2 + t + 2); issue_q(G2 + t + 2, t + 2); }
+                }
+            }
+        } else {
+            // ------------------------------------------------------------------------------------------- Cx: epilogue-consuming MMAs
+            uint32_t ph_w = 0;
+            for (int it = 0; it < n_img; ++it) {
+                for (int j = 0; j < J; ++j) {
+                    wait_edone(j & 1, kPass1Edone);              // P / V^T of chunk j written
+                    if (elect_one()) {
+                        const uint64_t ad = desc(sb + L::off_u + (j & 1) * L::kPBytes);
+                        const uint64_t bd = desc(sb + L::off_u + 2 * L::kPBytes + (j & 1) * L::kVBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256u, ad + 2u * k, bd + 2u * k, idesc_ctx, (j | k) ? 1u : 0u);
+                        umma_commit(&bars->pvdone[j & 1]);
+                    }
+                    __syncwarp();
+                    TR(12, j);
+                }
+                // between the passes: M[(h,d)][c] = ctx[(h,d)][(h',e)] . W_out[c][(h',e)]^T   (W_out sits in the M^T region)
+                named_bar_sync(kBarCdone, kEpiThreads + 32);      // block-diagonal context written (every context MMA retired)
+                TR(30, it);
+                wait_leader(&bars->woutfull, ph_w);
+                ph_w ^= 1u;
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const uint64_t ad = desc(sb + L::off_u + a * 16384);
+                        const uint64_t bd = desc(sb + L::off_mt + a * (C * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc_y, (a | k) ? 1u : 0u);
+                    }
+                    umma_commit(&bars->mdone);
+                }
+                __syncwarp();
+                TR(31, it);
+                named_bar_sync(kBarMtdone, kEpiThreads + 64);     // M^T written, its accumulator read out
+                tc_fence_after();
+                for (int t = 0; t < T; ++t) {
+                    wait_edone(t & 1, kPass2Edone);              // softmax(q) tile t written; Y accumulator t & 1 was read out two tiles ago
+                    if (elect_one()) {
+#pragma unroll
+                        for (int a = 0; a < 2; ++a) {
+                            const uint64_t ad = desc(sb + L::off_u + (t & 1) * 32768 + a * 16384);
+                            const uint64_t bd = desc(sb + L::off_mt + a * (C * 128));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tmem_base + 256u + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_y, (a | k) ? 1u : 0u);
+                        }
+                        umma_commit(&bars->yfull[t & 1]);
+                    }
+                    __syncwarp();
+                    TR(22, t);
+                }
+            }
         }
-        if (elect_one()) bulk_wait_group<0>();
-        __syncwarp();
     } else {
         // =============================================================================================== epilogue warps
-        // 16 warps: q = warp & 3 is the TMEM lane quarter (accumulator rows 32q .. 32q+31), part = warp >> 2 the column
-        // quarter.  Four warps per scheduler: the math of one warp hides the TMEM / shared-memory / MUFU latencies of the
-        // others (with 8 warps the kernel was latency-bound at one instruction per 7.7 cycles per warp).
+        // Two groups of 8 warps.  Group g owns the pass-1 chunks j with j & 1 == g and the pass-2 tiles t with t & 1 == g:
+        // accumulator buffer g, P / V^T buffer g, softmax(q) buffer g and Y accumulator g are its private property, so the
+        // two groups never synchronise with each other inside a pass and the fixed latencies of one (mbarrier poll, named
+        // barrier, fences, MMA round trip) are covered by the other's math.  Inside a group: q = lane quarter (accumulator
+        // rows 32q .. 32q+31), half = column half.  Only the group leader polls mbarriers (every poller slows the CTA's
+        // mbarrier traffic); the rest of the group learns through the group's named barrier.
+        const int grp = warp >> 3;
+        const int wg = warp & 7;
+        const int half = wg >> 2;
+        const int gtid = tid & (kGroupThreads - 1);
+        const bool leader = wg == 0 && lane == 0;
+        const int bar_g = kBarEpi + grp;
         const float* rn_f = rn_s;
         const float* rnl_f = rnl_s;
-        const bool leader = warp == 0 && lane == 0;       // the only mbarrier poller among the epilogue warps
-        auto arrive = [&](int bar_id) {     // this thread's generic-proxy writes / TMEM reads are done: tell the control warp
+        auto arrive = [&](int bar_id, int count) {     // this thread's generic-proxy writes / TMEM reads are done: tell the control warp
             fence_proxy_async();
             tc_fence_before();
-            named_bar_arrive(bar_id, kThreads);
+            named_bar_arrive(bar_id, count);
         };
         auto xbar = [&](int g) -> uint64_t* { return &bars->xfull[g % NB]; };
         auto xpar = [&](int g) -> uint32_t { return static_cast<uint32_t>(g / NB) & 1u; };
-        // per-token 1 / max(||x||, 1e-12) of tile g (the block's pre-norm, dd:176; gain is folded into W_qkv):
-        // four lanes per token, two 16-byte units each
-        auto rn_compute = [&](int g) {
+        auto poll_x = [&](int g) { if (leader) mbar_wait(xbar(g), xpar(g)); };
+        auto publish = [&]() { named_bar_sync(bar_g, kGroupThreads); tc_fence_after(); };     // what the leader saw holds for the group
+        // per-token 1 / max(||x||, 1e-12) (the block's pre-norm, dd:176; gain is folded into W_qkv) of `ntok` tokens starting at
+        // token `tok0` of tile g, by this group: 256 / ntok lanes per token
+        auto rn_compute = [&](int g, int tok0, int ntok) {
             const int slot = g % NB;
-            const int r = warp * 8 + (lane >> 2), sub = lane & 3;
+            const int lpt = kGroupThreads / ntok;                  // 4 (64-token chunk) or 2 (128-token tile)
+            const int r = tok0 + gtid / lpt, sub = gtid % lpt;
+            const int upl = 8 / lpt;                               // 16-byte units per lane
             float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
             for (int a = 0; a < kAtoms; ++a) {
                 const uint32_t base = sb + L::off_x + slot * L::kXTile + a * (kTileTok * 128) + r * 128;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const uint4 v = lds_128u(base + static_cast<uint32_t>(((2 * sub + k) ^ (r & 7)) << 4));      // any order: it is a sum
+                for (int k = 0; k < upl; ++k) {
+                    const uint4 v = lds_128u(base + static_cast<uint32_t>(((upl * sub + k) ^ (r & 7)) << 4));      // any order: it is a sum
                     s0 = fmaf(bf16_lo(v.x), bf16_lo(v.x), s0); s1 = fmaf(bf16_hi(v.x), bf16_hi(v.x), s1);
                     s0 = fmaf(bf16_lo(v.y), bf16_lo(v.y), s0); s1 = fmaf(bf16_hi(v.y), bf16_hi(v.y), s1);
                     s0 = fmaf(bf16_lo(v.z), bf16_lo(v.z), s0); s1 = fmaf(bf16_hi(v.z), bf16_hi(v.z), s1);
@@ -431,80 +444,81 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
             float ss = s0 + s1;
             ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            if (lpt == 4) ss += __shfl_xor_sync(0xffffffffu, ss, 2);
             if (sub == 0) {
                 const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
                 rn_s[slot * 128 + r] = rn;
                 rnl_s[slot * 128 + r] = rn * kLog2e;
             }
         };
-        uint32_t ph_acc = 0, ph_pv = 0, ph_y = 0, ph_m = 0;     // phase bits, one per barrier (tracked by every thread, used by the leader)
-        auto poll_acc = [&](int i) { if (leader) mbar_wait(&bars->accfull[i], (ph_acc >> i) & 1u); ph_acc ^= 1u << i; };
-        auto poll_pv = [&](int i) { if (leader) mbar_wait(&bars->pvdone[i], (ph_pv >> i) & 1u); ph_pv ^= 1u << i; };
-        auto poll_y = [&](int i) { if (leader) mbar_wait(&bars->yfull[i], (ph_y >> i) & 1u); ph_y ^= 1u << i; };
-        auto poll_x = [&](int g) { if (leader) mbar_wait(xbar(g), xpar(g)); };
-        auto publish = [&]() { named_bar_sync(kBarEpi, kEpiThreads); tc_fence_after(); };     // what the leader saw holds for all
+        uint32_t ph_acc = 0, ph_pv = 0, ph_y = 0, ph_m = 0;     // phases of THIS group's barriers (accfull[grp], pvdone[grp], yfull[grp])
 
         int G = 0;       // global tile index of the current image's first pass-1 tile
         for (int it = 0; it < n_img; ++it, G += 2 * T) {
             // ======================================================================================= pass 1
-            if (tid < 256) {   // the V^T buffers' extra rows: row 128 = ones (its context column is the sum of P), rows 129..143 = 0
-                const int vb = tid >> 7, r = (tid & 127) >> 3, u = tid & 7;
+            if (gtid < 128) {   // this group's V^T buffer: row 128 = ones (its context column is the sum of P), rows 129..143 = 0
+                const int r = gtid >> 3, u = gtid & 7;
                 const uint32_t one2 = r == 0 ? 0x3F803F80u : 0u;
-                sts_128u(sb + L::off_u + 2 * L::kPBytes + vb * L::kVBytes + (128 + r) * 128 + u * 16, one2, one2, one2, one2);
-                // published to the context MMA by the fence + arrival that follows chunk 0 (edone)
+                sts_128u(sb + L::off_u + 2 * L::kPBytes + grp * L::kVBytes + (128 + r) * 128 + u * 16, one2, one2, one2, one2);
+                // published to the context MMA by the fence + arrival that follows this group's first chunk (edone)
             }
             poll_x(G);
             publish();
-            rn_compute(G);            // published by the barrier that opens chunk 0
-            for (int j = 0; j < J; ++j) {
+            rn_compute(G, grp * kChunkTok, kChunkTok);            // own first chunk; published by the barrier that opens it
+            for (int j = grp; j < J; j += 2) {
                 const int gt = G + (j >> 1);
-                if ((j & 1) && j + 1 < J) poll_x(gt + 1);      // the next tile, for its norms at the end of this chunk
-                poll_acc(j & 1);
-                if (j >= 2) poll_pv(j & 1);
+                if (j + 2 < J) poll_x(gt + 1);                    // the tile of this group's next chunk, for its norms
+                if (leader) mbar_wait(&bars->accfull[grp], ph_acc);
+                ph_acc ^= 1u;
+                if (j >= 2) { if (leader) mbar_wait(&bars->pvdone[grp], ph_pv); ph_pv ^= 1u; }
                 publish();
                 TR(4, j);
-                {   // epilogue: thread = channel `row`; tokens part*16 .. +15 of the chunk
+                {   // epilogue: thread = channel `row`; tokens half*32 .. +31 of the chunk, in two halves of 16 (register budget)
                     const int slot = gt % NB;
-                    const uint32_t accb = t_lane + static_cast<uint32_t>((j & 1) * 128 + part * 16);
-                    uint32_t kr[16], vr[16];
-                    tmem_ld16(accb, kr);
-                    tmem_ld16(accb + 64u, vr);
-                    const int tok0 = slot * 128 + (j & 1) * 64 + part * 16;
-                    float al[16], bl[16];
+                    const uint32_t prow = sb + L::off_u + grp * L::kPBytes + row * 128;
+                    const uint32_t vrow = sb + L::off_u + 2 * L::kPBytes + grp * L::kVBytes + row * 128;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(rnl_f + tok0 + 4 * i);
-                        const float4 b4 = *reinterpret_cast<const float4*>(rn_f + tok0 + 4 * i);
-                        al[4 * i] = a4.x; al[4 * i + 1] = a4.y; al[4 * i + 2] = a4.z; al[4 * i + 3] = a4.w;
-                        bl[4 * i] = b4.x; bl[4 * i + 1] = b4.y; bl[4 * i + 2] = b4.z; bl[4 * i + 3] = b4.w;
-                    }
-                    tmem_ld_wait();
-                    const uint32_t prow = sb + L::off_u + (j & 1) * L::kPBytes + row * 128;
-                    const uint32_t vrow = sb + L::off_u + 2 * L::kPBytes + (j & 1) * L::kVBytes + row * 128;
-                    uint32_t pw[8], vw[8];
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const uint32_t accb = t_lane + static_cast<uint32_t>(grp * 128 + half * 32 + hh * 16);
+                        uint32_t kr[16], vr[16];
+                        tmem_ld16(accb, kr);
+                        tmem_ld16(accb + 64u, vr);
+                        const int tok0 = slot * 128 + grp * 64 + half * 32 + hh * 16;
+                        float al[16], bl[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(kr[2 * i]), al[2 * i], -mcl));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(kr[2 * i + 1]), al[2 * i + 1], -mcl));
-                        pw[i] = pack_bf16x2(p0, p1);
-                        vw[i] = pack_bf16x2(__uint_as_float(vr[2 * i]) * bl[2 * i], __uint_as_float(vr[2 * i + 1]) * bl[2 * i + 1]);
-                    }
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(rnl_f + tok0 + 4 * i);
+                            const float4 b4 = *reinterpret_cast<const float4*>(rn_f + tok0 + 4 * i);
+                            al[4 * i] = a4.x; al[4 * i + 1] = a4.y; al[4 * i + 2] = a4.z; al[4 * i + 3] = a4.w;
+                            bl[4 * i] = b4.x; bl[4 * i + 1] = b4.y; bl[4 * i + 2] = b4.z; bl[4 * i + 3] = b4.w;
+                        }
+                        tmem_ld_wait();
+                        uint32_t pw[8], vw[8];
 #pragma unroll
-                    for (int g2 = 0; g2 < 2; ++g2) {
-                        const uint32_t uo = static_cast<uint32_t>(((part * 2 + g2) ^ sw) << 4);
-                        sts_128u(prow + uo, pw[4 * g2], pw[4 * g2 + 1], pw[4 * g2 + 2], pw[4 * g2 + 3]);
-                        sts_128u(vrow + uo, vw[4 * g2], vw[4 * g2 + 1], vw[4 * g2 + 2], vw[4 * g2 + 3]);
+                        for (int i = 0; i < 8; ++i) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(kr[2 * i]), al[2 * i], -mcl));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(kr[2 * i + 1]), al[2 * i + 1], -mcl));
+                            pw[i] = pack_bf16x2(p0, p1);
+                            vw[i] = pack_bf16x2(__uint_as_float(vr[2 * i]) * bl[2 * i], __uint_as_float(vr[2 * i + 1]) * bl[2 * i + 1]);
+                        }
+#pragma unroll
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            const uint32_t uo = static_cast<uint32_t>(((half * 4 + hh * 2 + g2) ^ sw) << 4);
+                            sts_128u(prow + uo, pw[4 * g2], pw[4 * g2 + 1], pw[4 * g2 + 2], pw[4 * g2 + 3]);
+                            sts_128u(vrow + uo, vw[4 * g2], vw[4 * g2 + 1], vw[4 * g2 + 2], vw[4 * g2 + 3]);
+                        }
                     }
                 }
                 TR(5, j);
-                arrive(kBarEdone + (j & 1));
-                if ((j & 1) && j + 1 < J) rn_compute(gt + 1);
+                arrive(kBarEdone + grp, kPass1Edone);        // (the tile of this chunk is not read again: its norms were taken before)
+                if (j + 2 < J) rn_compute(gt + 1, grp * kChunkTok, kChunkTok);
                 TR(6, j);
             }
-            poll_pv(J & 1);            // chunk J-2
-            poll_pv((J - 1) & 1);      // chunk J-1: the context is complete
-            publish();
+            // this group's last context MMA (chunk J - 2 + grp), then both groups meet: the context is complete
+            if (leader) mbar_wait(&bars->pvdone[grp], ph_pv);
+            ph_pv ^= 1u;
+            named_bar_sync(kBarAll, kEpiThreads);
+            tc_fence_after();
             TR(50, it);
 
             // ======================================================================================= between the passes
@@ -544,11 +558,12 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     else sts_128u(addr, 0u, 0u, 0u, 0u);
                 }
             }
-            arrive(kBarCdone);
+            arrive(kBarCdone, kEpiThreads + 32);
             TR(51, it);
-            if (leader) mbar_wait(&bars->mdone, ph_m);
+            if (warp == 0 && lane == 0) mbar_wait(&bars->mdone, ph_m);
             ph_m ^= 1u;
-            publish();
+            named_bar_sync(kBarAll, kEpiThreads);
+            tc_fence_after();
             TR(52, it);
             {   // thread = row (h,d) of M; columns c = part * C/4 .. ; stored transposed as M^T[c][(h,d)] (K-major B operand of Y)
                 constexpr int kMc = C / 4;
@@ -565,108 +580,118 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(mbase + c * 128 + static_cast<uint32_t>((ku ^ (c & 7)) << 4)), "h"(hv) : "memory");
                 }
             }
-            arrive(kBarMtdone);
+            arrive(kBarMtdone, kEpiThreads + 64);
             TR(53, it);
 
             // ======================================================================================= pass 2
             const int G2 = G + T;
-            auto epilogue_y = [&](int u_t) {     // its yfull was polled and published by the caller
-                TR(45, u_t);
-                const int slot = (G2 + u_t) % NB;
-                constexpr int kCols = C / 4;                      // columns of this thread: part * kCols .. +kCols-1
-                static_assert(kCols == 16, "Y epilogue is written for C = 64");
-                uint32_t yr[16];
-                tmem_ld16(t_lane + 256u + static_cast<uint32_t>((u_t & 1) * 128 + part * kCols), yr);
-                // residual x (own row of the tile); the result is written in place.  column c: atom c / 64, unit (c % 64) / 8
-                const uint32_t xrow = sb + L::off_x + slot * L::kXTile + row * 128;
-                const uint32_t a0 = xrow + static_cast<uint32_t>(((part * 2) ^ sw) << 4), a1 = xrow + static_cast<uint32_t>(((part * 2 + 1) ^ sw) << 4);
-                const uint4 x0 = lds_128u(a0), x1 = lds_128u(a1);
-                const float4* bp = reinterpret_cast<const float4*>(bias_s + part * kCols);
-                const float4* gp = reinterpret_cast<const float4*>(g_s + part * kCols);
-                float v[16];
-                tmem_ld_wait();
-                float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 bb = bp[i];
-                    v[4 * i] = __uint_as_float(yr[4 * i]) + bb.x;
-                    v[4 * i + 1] = __uint_as_float(yr[4 * i + 1]) + bb.y;
-                    v[4 * i + 2] = __uint_as_float(yr[4 * i + 2]) + bb.z;
-                    v[4 * i + 3] = __uint_as_float(yr[4 * i + 3]) + bb.w;
-                    s0 = fmaf(v[4 * i], v[4 * i], s0); s1 = fmaf(v[4 * i + 1], v[4 * i + 1], s1);
-                    s0 = fmaf(v[4 * i + 2], v[4 * i + 2], s0); s1 = fmaf(v[4 * i + 3], v[4 * i + 3], s1);
-                }
-                float* red = red_s + (u_t & 1) * 512;
-                red[part * 128 + row] = s0 + s1;
-                tc_fence_before();
-                named_bar_sync(kBarEpi, kEpiThreads);
-                TR(46, u_t);
-                const float rinv = 1.0f / fmaxf(sqrtf((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])), 1e-12f);
-                const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
-                sts_128u(a0, pack_bf16x2(fmaf(v[0] * rinv, g0.x, bf16_lo(x0.x)), fmaf(v[1] * rinv, g0.y, bf16_hi(x0.x))),
-                         pack_bf16x2(fmaf(v[2] * rinv, g0.z, bf16_lo(x0.y)), fmaf(v[3] * rinv, g0.w, bf16_hi(x0.y))),
-                         pack_bf16x2(fmaf(v[4] * rinv, g1.x, bf16_lo(x0.z)), fmaf(v[5] * rinv, g1.y, bf16_hi(x0.z))),
-                         pack_bf16x2(fmaf(v[6] * rinv, g1.z, bf16_lo(x0.w)), fmaf(v[7] * rinv, g1.w, bf16_hi(x0.w))));
-                sts_128u(a1, pack_bf16x2(fmaf(v[8] * rinv, g2.x, bf16_lo(x1.x)), fmaf(v[9] * rinv, g2.y, bf16_hi(x1.x))),
-                         pack_bf16x2(fmaf(v[10] * rinv, g2.z, bf16_lo(x1.y)), fmaf(v[11] * rinv, g2.w, bf16_hi(x1.y))),
-                         pack_bf16x2(fmaf(v[12] * rinv, g3.x, bf16_lo(x1.z)), fmaf(v[13] * rinv, g3.y, bf16_hi(x1.z))),
-                         pack_bf16x2(fmaf(v[14] * rinv, g3.z, bf16_lo(x1.w)), fmaf(v[15] * rinv, g3.w, bf16_hi(x1.w))));
-                arrive(kBarYdone + (u_t & 1));
-                TR(47, u_t);
-            };
-
-            poll_x(G2);
-            publish();
-            rn_compute(G2);           // published by the barrier that opens tile 0
-            for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) poll_x(G2 + t + 1);
-                poll_acc(t & 1);
-                if (t >= 1) poll_y((t - 1) & 1);
+            if (grp < T) {
+                poll_x(G2 + grp);
+                publish();
+                rn_compute(G2 + grp, 0, kTileTok);      // own first tile; published by the barrier that opens it
+            }
+            for (int t = grp; t < T; t += 2) {
+                const int slot = (G2 + t) % NB;
+                if (leader) mbar_wait(&bars->accfull[grp], ph_acc);
+                ph_acc ^= 1u;
                 publish();
                 TR(42, t);
-                {   // epilogue: thread = token `row`, head `part`: softmax over its 32 channels (dd:184)
-                    const int slot = (G2 + t) % NB;
+                {   // Q epilogue: thread = token `row`; heads 2*half, 2*half+1: softmax over the 32 channels of each (dd:184)
                     const float rnl = rnl_f[slot * 128 + row];
-                    uint32_t qr[32];
-                    tmem_ld32(t_lane + static_cast<uint32_t>((t & 1) * 128 + part * 32), qr);
-                    tmem_ld_wait();
-                    float m0 = fmaxf(__uint_as_float(qr[0]), __uint_as_float(qr[1])), m1 = fmaxf(__uint_as_float(qr[2]), __uint_as_float(qr[3]));
-                    float m2 = fmaxf(__uint_as_float(qr[4]), __uint_as_float(qr[5])), m3 = fmaxf(__uint_as_float(qr[6]), __uint_as_float(qr[7]));
+                    const uint32_t qrow = sb + L::off_u + grp * 32768 + half * 16384 + row * 128;
 #pragma unroll
-                    for (int i = 8; i < 32; i += 8) {
-                        m0 = fmaxf(m0, fmaxf(__uint_as_float(qr[i]), __uint_as_float(qr[i + 1])));
-                        m1 = fmaxf(m1, fmaxf(__uint_as_float(qr[i + 2]), __uint_as_float(qr[i + 3])));
-                        m2 = fmaxf(m2, fmaxf(__uint_as_float(qr[i + 4]), __uint_as_float(qr[i + 5])));
-                        m3 = fmaxf(m3, fmaxf(__uint_as_float(qr[i + 6]), __uint_as_float(qr[i + 7])));
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t qr[32];
+                        tmem_ld32(t_lane + static_cast<uint32_t>(grp * 128 + half * 64 + hh * 32), qr);
+                        tmem_ld_wait();
+                        float m0 = fmaxf(__uint_as_float(qr[0]), __uint_as_float(qr[1])), m1 = fmaxf(__uint_as_float(qr[2]), __uint_as_float(qr[3]));
+                        float m2 = fmaxf(__uint_as_float(qr[4]), __uint_as_float(qr[5])), m3 = fmaxf(__uint_as_float(qr[6]), __uint_as_float(qr[7]));
+#pragma unroll
+                        for (int i = 8; i < 32; i += 8) {
+                            m0 = fmaxf(m0, fmaxf(__uint_as_float(qr[i]), __uint_as_float(qr[i + 1])));
+                            m1 = fmaxf(m1, fmaxf(__uint_as_float(qr[i + 2]), __uint_as_float(qr[i + 3])));
+                            m2 = fmaxf(m2, fmaxf(__uint_as_float(qr[i + 4]), __uint_as_float(qr[i + 5])));
+                            m3 = fmaxf(m3, fmaxf(__uint_as_float(qr[i + 6]), __uint_as_float(qr[i + 7])));
+                        }
+                        const float mm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * rnl;
+                        float e[32];
+                        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            e[i] = ex2_approx(fmaf(__uint_as_float(qr[i]), rnl, -mm));
+                            e[i + 1] = ex2_approx(fmaf(__uint_as_float(qr[i + 1]), rnl, -mm));
+                            e[i + 2] = ex2_approx(fmaf(__uint_as_float(qr[i + 2]), rnl, -mm));
+                            e[i + 3] = ex2_approx(fmaf(__uint_as_float(qr[i + 3]), rnl, -mm));
+                            s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
+                        }
+                        const float inv = 1.0f / ((s0 + s1) + (s2 + s3));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            sts_128u(qrow + static_cast<uint32_t>(((hh * 4 + u) ^ sw) << 4),
+                                     pack_bf16x2(e[8 * u] * inv, e[8 * u + 1] * inv), pack_bf16x2(e[8 * u + 2] * inv, e[8 * u + 3] * inv),
+                                     pack_bf16x2(e[8 * u + 4] * inv, e[8 * u + 5] * inv), pack_bf16x2(e[8 * u + 6] * inv, e[8 * u + 7] * inv));
                     }
-                    const float mm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * rnl;
-                    float e[32];
-                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        e[i] = ex2_approx(fmaf(__uint_as_float(qr[i]), rnl, -mm));
-                        e[i + 1] = ex2_approx(fmaf(__uint_as_float(qr[i + 1]), rnl, -mm));
-                        e[i + 2] = ex2_approx(fmaf(__uint_as_float(qr[i + 2]), rnl, -mm));
-                        e[i + 3] = ex2_approx(fmaf(__uint_as_float(qr[i + 3]), rnl, -mm));
-                        s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
-                    }
-                    const float inv = 1.0f / ((s0 + s1) + (s2 + s3));
-                    const uint32_t qrow = sb + L::off_u + (t & 1) * 32768 + (part >> 1) * 16384 + row * 128;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        sts_128u(qrow + static_cast<uint32_t>((((part & 1) * 4 + u) ^ sw) << 4),
-                                 pack_bf16x2(e[8 * u] * inv, e[8 * u + 1] * inv), pack_bf16x2(e[8 * u + 2] * inv, e[8 * u + 3] * inv),
-                                 pack_bf16x2(e[8 * u + 4] * inv, e[8 * u + 5] * inv), pack_bf16x2(e[8 * u + 6] * inv, e[8 * u + 7] * inv));
                 }
                 TR(43, t);
-                arrive(kBarEdone + (t & 1));
+                arrive(kBarEdone + grp, kPass2Edone);
                 TR(44, t);
-                if (t + 1 < T) rn_compute(G2 + t + 1);      // published by epilogue_y's barrier / the next tile's opening barrier
-                if (t >= 1) epilogue_y(t - 1);
+                // Y epilogue of the same tile: the Y MMA is issued as soon as the control warp sees the arrival above
+                if (leader) mbar_wait(&bars->yfull[grp], ph_y);
+                ph_y ^= 1u;
+                publish();
+                TR(45, t);
+                {
+                    constexpr int kCols = C / 2;                      // columns of this thread: half * kCols .. +kCols-1
+                    static_assert(kCols == 32, "Y epilogue is written for C = 64");
+                    uint32_t yr[32];
+                    tmem_ld32(t_lane + 256u + static_cast<uint32_t>(grp * 128 + half * kCols), yr);
+                    // residual x (own row of the tile); the result is written in place.  column c: atom c / 64, unit (c % 64) / 8
+                    const uint32_t xrow = sb + L::off_x + slot * L::kXTile + row * 128;
+                    uint4 xr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xr[u] = lds_128u(xrow + static_cast<uint32_t>(((half * 4 + u) ^ sw) << 4));
+                    const float4* bp = reinterpret_cast<const float4*>(bias_s + half * kCols);
+                    const float4* gp = reinterpret_cast<const float4*>(g_s + half * kCols);
+                    float v[32];
+                    tmem_ld_wait();
+                    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bb = bp[i];
+                        v[4 * i] = __uint_as_float(yr[4 * i]) + bb.x;
+                        v[4 * i + 1] = __uint_as_float(yr[4 * i + 1]) + bb.y;
+                        v[4 * i + 2] = __uint_as_float(yr[4 * i + 2]) + bb.z;
+                        v[4 * i + 3] = __uint_as_float(yr[4 * i + 3]) + bb.w;
+                        s0 = fmaf(v[4 * i], v[4 * i], s0); s1 = fmaf(v[4 * i + 1], v[4 * i + 1], s1);
+                        s0 = fmaf(v[4 * i + 2], v[4 * i + 2], s0); s1 = fmaf(v[4 * i + 3], v[4 * i + 3], s1);
+                    }
+                    float* red = red_s + grp * 256;
+                    red[half * 128 + row] = s0 + s1;
+                    tc_fence_before();
+                    named_bar_sync(bar_g, kGroupThreads);
+                    TR(46, t);
+                    const float rinv = 1.0f / fmaxf(sqrtf(red[row] + red[128 + row]), 1e-12f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 g0 = gp[2 * u], g1 = gp[2 * u + 1];
+                        const float* vv = v + 8 * u;
+                        sts_128u(xrow + static_cast<uint32_t>(((half * 4 + u) ^ sw) << 4),
+                                 pack_bf16x2(fmaf(vv[0] * rinv, g0.x, bf16_lo(xr[u].x)), fmaf(vv[1] * rinv, g0.y, bf16_hi(xr[u].x))),
+                                 pack_bf16x2(fmaf(vv[2] * rinv, g0.z, bf16_lo(xr[u].y)), fmaf(vv[3] * rinv, g0.w, bf16_hi(xr[u].y))),
+                                 pack_bf16x2(fmaf(vv[4] * rinv, g1.x, bf16_lo(xr[u].z)), fmaf(vv[5] * rinv, g1.y, bf16_hi(xr[u].z))),
+                                 pack_bf16x2(fmaf(vv[6] * rinv, g1.z, bf16_lo(xr[u].w)), fmaf(vv[7] * rinv, g1.w, bf16_hi(xr[u].w))));
+                    }
+                }
+                arrive(kBarYdone + (t & 3), kGroupThreads + 32);
+                TR(47, t);
+                if (t + 2 < T) {        // own next tile: its norms now (the ring has had a whole tile time to deliver it)
+                    poll_x(G2 + t + 2);
+                    publish();
+                    rn_compute(G2 + t + 2, 0, kTileTok);      // published by the barrier that opens that tile
+                }
             }
-            poll_y((T - 1) & 1);
-            publish();
-            epilogue_y(T - 1);
+            // both groups leave the pass together: the next image's first chunk epilogue reuses the union region / rn slots
+            named_bar_sync(kBarAll, kEpiThreads);
         }
     }
     tc_fence_before();
