@@ -18,6 +18,10 @@ void launch_linattn_fused(const CUtensorMap& tmX, const CUtensorMap& tmY, const 
                           const float* bias_out, const float* g_out, const float* mem_kv, const float* k_shift, int B, int n, int C,
                           int n_mem, int num_sms, int trace, cudaStream_t s);
 int linattn_trace_read(long long* host, int cap);
+int attention_tc_prepare_attributes();
+bool attention_tc_supported(int d, int n_mem);
+void launch_attention_tc(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const float* mem_k, const float* mem_v,
+                         int n_mem, void* out, int B, int nq, int nk, int heads, int d, cudaStream_t s);
 }
 
 namespace {
@@ -27,6 +31,7 @@ int g_num_sms = 0;
 bool g_ready = false;
 int g_conv_debug = 0;
 int g_laf_trace = 0;
+bool g_tc_attention = true;
 std::atomic<long long> g_launches{0};
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -111,6 +116,9 @@ static int init_on_current_device(int device) {
     if (r != 0) return r;
     r = ddm::linattn_fused_prepare_attributes();
     if (r != 0) return r;
+    r = ddm::attention_tc_prepare_attributes();
+    if (r != 0) return r;
+    if (std::getenv("DDM_NO_TC_ATTENTION")) g_tc_attention = false;      // A/B timing against the CUDA-core kernel
     if (const char* t = std::getenv("DDM_LAF_TRACE")) g_laf_trace = std::atoi(t);       // scripts/laf_trace.py
     if (const char* dbg = std::getenv("DDM_CONV_DEBUG")) g_conv_debug = std::atoi(dbg);   // bottleneck bisection, see conv_tc.cuh
     g_ready = true;
@@ -497,6 +505,23 @@ int ddm_attention(const void* q, int ldq, const void* k, int ldk, const void* v,
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out_bf16) || (ldq % 8) || (ldk % 8) || (ldv % 8))
         return DDM_E_ALIGNMENT;
     if (B > 65535 || heads > 65535 || n_mem < 0 || n_mem > 64) return DDM_E_UNSUPPORTED;
+    if (g_tc_attention && ddm::attention_tc_supported(d, n_mem) && static_cast<long long>(B) * (nq > nk ? nq : nk) < 0x7FFFFFFFll) {
+        // tcgen05 path: S = Q K^T and O = P V on the tensor cores (attention_tc.cu)
+        CUtensorMap tmQ, tmK, tmV;
+        const unsigned box[2] = {64u, 128u};
+        const unsigned long long w = static_cast<unsigned long long>(heads) * d;
+        auto enc = [&](CUtensorMap* tm, const void* base, int ld, long long rows) -> int {
+            const unsigned long long dims[2] = {w, static_cast<unsigned long long>(rows)};
+            const unsigned long long str[2] = {1ull, static_cast<unsigned long long>(ld)};
+            return encode_bf16_map(tm, base, 2, dims, str, box);
+        };
+        int e = enc(&tmQ, q, ldq, static_cast<long long>(B) * nq);
+        if (e == 0) e = enc(&tmK, k, ldk, static_cast<long long>(B) * nk);
+        if (e == 0) e = enc(&tmV, v, ldv, static_cast<long long>(B) * nk);
+        if (e != 0) return e;
+        ddm::launch_attention_tc(tmQ, tmK, tmV, mem_k, mem_v, n_mem, out_bf16, B, nq, nk, heads, d, as_stream(stream));
+        return finish(1);
+    }
     const int r = ddm::launch_attention(q, ldq, k, ldk, v, ldv, mem_k, mem_v, n_mem, out_bf16, B, nq, nk, heads, d, as_stream(stream));
     return r != 0 ? r : finish(1);
 }

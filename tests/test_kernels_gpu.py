@@ -346,9 +346,14 @@ def test_linear_attention_block_fused(lib, B, n, wscale, n_mem):
 
 
 @pytest.mark.parametrize("nq,nk,heads,d,n_mem", [(16, 16, 4, 32, 4), (64, 64, 4, 32, 4), (256, 256, 4, 32, 4), (64, 77, 4, 32, 0),
-                                                 (16, 1, 4, 32, 0), (16, 16, 2, 16, 4)])
+                                                 (16, 1, 4, 32, 0), (16, 16, 2, 16, 4), (256, 256, 1, 128, 0), (100, 300, 2, 64, 3),
+                                                 (1024, 1024, 1, 128, 0), (16, 16, 4, 32, 16)])
 def test_softmax_attention(lib, nq, nk, heads, d, n_mem):
-    B, hd = 3, heads * d
+    """ddm_attention: tcgen05 kernel (d = 32 / 64 / 128; tiles spanning several images, several key tiles, memory keys) and the
+    CUDA-core kernel (d = 16)."""
+    B, hd = (3 if nq <= 256 else 2), heads * d
+    if nq == 16 and nk == 16 and n_mem == 4 and d == 32:
+        B = 37                  # 592 query rows: 4 full tiles of 8 images + a ragged one
     q, k, v = (dev(rnd((B, n_, hd), 130 + i), BF) for i, n_ in enumerate((nq, nk, nk)))
     mk, mv = (dev(rnd((heads, max(n_mem, 1), d), 135 + i)) for i in range(2))
     out = torch.zeros((B, nq, hd), dtype=BF, device="cuda")
