@@ -17,10 +17,11 @@ from .latent import LatentDiffusion, ImageConditionalLatentDiffusion, TextCondit
 from .ddim_sampler import DDIMSampler
 from .learned_gaussian import LearnedGaussianDiffusion
 from .distributed import sample_sharded, shard_bounds, gather_samples
+from .vae import VQDecoder
 from .trainer_adapter import attach_fast_sampler, FastSamplerBinding
-from . import image_conditional, text_conditional, latent, sampling, trainer_adapter, _lib
+from . import image_conditional, text_conditional, latent, sampling, trainer_adapter, vae, _lib
 
 __version__ = "0.1.0"
 __all__ = ["Unet", "DenoisingDiffusion", "GaussianDiffusion", "ModelPrediction", "ImageConditionalDenoisingDiffusion",
            "TextConditionalDenoisingDiffusion", "LatentDiffusion", "ImageConditionalLatentDiffusion",
-           "TextConditionalLatentDiffusion", "DDIMSampler", "LearnedGaussianDiffusion", "sample_sharded", "shard_bounds", "gather_samples", "attach_fast_sampler", "FastSamplerBinding"]
+           "TextConditionalLatentDiffusion", "DDIMSampler", "LearnedGaussianDiffusion", "sample_sharded", "shard_bounds", "gather_samples", "attach_fast_sampler", "FastSamplerBinding", "VQDecoder"]

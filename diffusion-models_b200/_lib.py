@@ -70,6 +70,8 @@ EXPORTS = {
     "ddm_row_rnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "ddm_rmsnorm_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "ddm_groupnorm_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                    C.c_void_p]),
     "ddm_linear_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]),
     "ddm_linear_attention_block_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

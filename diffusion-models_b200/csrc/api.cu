@@ -450,6 +450,15 @@ int ddm_rmsnorm_act(const void* x_bf16, const float* norm_g, const float* scale_
     return finish(1);
 }
 
+int ddm_groupnorm_act(const void* x_bf16, const float* gamma, const float* beta, void* out_bf16, int B, int HW, int C, int groups, float eps,
+                      int act, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (x_bf16 == nullptr || gamma == nullptr || beta == nullptr || out_bf16 == nullptr || B < 1 || HW < 1 || B > 0x7FFFFFF) return DDM_E_BAD_ARGUMENT;
+    if (!aligned16(x_bf16) || !aligned16(out_bf16)) return DDM_E_ALIGNMENT;
+    const int r = ddm::launch_groupnorm_act(x_bf16, gamma, beta, out_bf16, B, HW, C, groups, eps, act, as_stream(stream));
+    return r != 0 ? DDM_E_UNSUPPORTED : finish(1);
+}
+
 int ddm_linear_attention(const void* qkv_bf16, const float* mem_kv, void* out_bf16, int B, int n, int heads, int d,
                          int n_mem, void* stream) {
     if (!g_ready) return DDM_E_NOT_INITIALISED;

@@ -47,11 +47,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trapped launch (cudaErrorLaunchFailure), never a hung GPU.
+// Bounded wait: a protocol bug becomes a trapped launch (cudaErrorLaunchFailure) after ~2 s, never a hung GPU.  (A spin
+// COUNT is not a bound: a failing try_wait may park the thread for a long, system-dependent time.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) { __trap(); }
+        if (clock64() - t0 > 4000000000ll) { __trap(); }
     }
 }
 

@@ -251,6 +251,85 @@ rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     for (int c = (sub + kKeep * lpr) * 8; c < C; c += lpr * 8) finish(c, __ldg(reinterpret_cast<const uint4*>(xr + c)));
 }
 
+// ------------------------------------------------------------------------------------------------ GroupNorm (+ swish)
+// VAE decoder norm (ldm/modules/diffusionmodules/model.py:55-56 Normalize = GroupNorm(32, C, eps=1e-6, affine) and the
+// x * sigmoid(x) that follows it at :118-119, :127-128, :573-574).  The statistics span a whole image (H*W x C/G values per
+// group), so this is a pre-pass in front of the tcgen05 conv rather than part of its epilogue: one CTA per image, two sweeps
+// over its bf16 channels-last activations (the second one from L2).
+__global__ void __launch_bounds__(512)
+groupnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ out, int HW, int C, int G, float eps, int act) {
+    extern __shared__ float gsm[];            // [C] sum | [C] sum of squares -> reused as [C] scale | [C] shift ; then [G] mean | [G] rstd
+    float* ch_a = gsm;
+    float* ch_b = gsm + C;
+    float* g_mean = gsm + 2 * C;
+    float* g_rstd = g_mean + G;
+    const int tid = threadIdx.x;
+    const __nv_bfloat16* xb = x + static_cast<long long>(blockIdx.x) * HW * C;
+    __nv_bfloat16* ob = out + static_cast<long long>(blockIdx.x) * HW * C;
+    const int nvec = C >> 3;                  // 16-byte vectors per pixel
+    const int rstep = blockDim.x / nvec;      // pixels in flight per sweep step
+    const int v = tid % nvec, r0 = tid / nvec;
+    const bool live = r0 < rstep;
+    for (int c = tid; c < 2 * C; c += blockDim.x) gsm[c] = 0.0f;
+    __syncthreads();
+    if (live) {
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = 0.0f; q[j] = 0.0f; }
+        for (int row = r0; row < HW; row += rstep) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(row) * C) + v);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = bf16_lo(w[j]), b2 = bf16_hi(w[j]);
+                s[2 * j] += a; s[2 * j + 1] += b2;
+                q[2 * j] = fmaf(a, a, q[2 * j]); q[2 * j + 1] = fmaf(b2, b2, q[2 * j + 1]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(ch_a + v * 8 + j, s[j]); atomicAdd(ch_b + v * 8 + j, q[j]); }
+    }
+    __syncthreads();
+    const int cg = C / G;
+    if (tid < G) {
+        float s = 0.0f, q = 0.0f;
+        for (int c = tid * cg; c < (tid + 1) * cg; ++c) { s += ch_a[c]; q += ch_b[c]; }
+        const float inv_n = 1.0f / (static_cast<float>(HW) * static_cast<float>(cg));
+        const float mean = s * inv_n;
+        const float var = fmaxf(q * inv_n - mean * mean, 0.0f);          // biased variance, like torch.nn.GroupNorm
+        g_mean[tid] = mean;
+        g_rstd[tid] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+        const int g = c / cg;
+        const float sc = __ldg(gamma + c) * g_rstd[g];
+        ch_a[c] = sc;
+        ch_b[c] = __ldg(beta + c) - g_mean[g] * sc;
+    }
+    __syncthreads();
+    if (!live) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = ch_a[v * 8 + j]; sh[j] = ch_b[v * 8 + j]; }
+    for (int row = r0; row < HW; row += rstep) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(row) * C) + v);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { f[2 * j] = bf16_lo(w[j]); f[2 * j + 1] = bf16_hi(w[j]); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = fmaf(f[j], sc[j], sh[j]);
+            if (act == 1) t = __fdividef(t, 1.0f + __expf(-t));
+            f[j] = t;
+        }
+        *(reinterpret_cast<uint4*>(ob + static_cast<long long>(row) * C) + v) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ head conv
 // final_conv (1x1, C -> N <= 8, denoising_diffusion.py:343,390): bf16 channels-last rows -> fp32 NCHW planes.
 // HBM-bound (reads 2*C bytes per pixel): `lpr` lanes share a pixel with 16-byte loads, shuffle-reduce, coalesced plane
@@ -536,6 +615,16 @@ void launch_rmsnorm_act(const void* x, const float* g, const float* ss, long lon
     rmsnorm_act_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), g, ss, ss_stride,
                                                           rows_per_batch, act, reinterpret_cast<const __nv_bfloat16*>(res),
                                                           reinterpret_cast<__nv_bfloat16*>(out), rows, C);
+}
+int launch_groupnorm_act(const void* x, const float* gamma, const float* beta, void* out, int B, int HW, int C, int G, float eps, int act,
+                         cudaStream_t s) {
+    const int nvec = C / 8;
+    if (C % 8 != 0 || nvec > 512 || G < 1 || G > 512 || C % G != 0) return -3;
+    const int smem = (2 * C + 2 * G) * 4;
+    if (smem > 48 * 1024) return -3;
+    groupnorm_act_kernel<<<B, 512, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), HW,
+                                              C, G, eps, act);
+    return 0;
 }
 int launch_head_conv(const void* x, const float* w, const float* bias, float* out, long long rows, int C, int N, int HW,
                      cudaStream_t s) {

@@ -28,35 +28,23 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-class UnetEngine:
-    def __init__(self, spec: UnetSpec, weights: Dict[str, torch.Tensor], batch: int, height: int, width: int,
-                 device: torch.device, time_rows: int = 1, text_tokens: int = 0, fuse_rnorm: bool = True, lib=None):
-        """`time_rows` is 1 when every sample shares the timestep (sampling loops, dd:641,682) or `batch`."""
-        assert height % spec.downsample_factor == 0 and width % spec.downsample_factor == 0, \
-            f"your input dimensions {(height, width)} need to be divisible by {spec.downsample_factor}, given the unet"
-        assert time_rows in (1, batch)
-        self.spec, self.B, self.H, self.W = spec, batch, height, width
+class PlanOps:
+    """Plan-building helpers shared by the kernel plans (U-Net forward here, VAE decode in vae.py): device tensors kept alive
+    for the raw pointers baked into the launch list, activation buffers, and the ddm_conv2d argument struct.  A plan owner
+    provides `device`, `lib`, `_keep`, `ops`, `taps`, `op_meta` and the fp32 master weights `_w`."""
+
+    def _init_plan(self, device, lib):
         self.device = torch.device(device)
-        # `lib` is a test seam (the CPU test-suite injects a stand-in that checks the host logic of a plan);
-        # the product always binds the real shared library and needs a B200.
-        if lib is not None:
+        if lib is not None:            # test seam: the CPU test-suite injects a stand-in that checks the host logic of a plan
             self.lib = lib
         else:
             if self.device.type != "cuda":
-                raise RuntimeError("UnetEngine needs a CUDA (B200) device: there is no CPU fallback")
+                raise RuntimeError("the kernel plans need a CUDA (B200) device: there is no CPU fallback")
             self.lib = _lib.init(self.device.index if self.device.index is not None else torch.cuda.current_device())
-        self.time_rows = time_rows
-        self.text_tokens = text_tokens
-        self.fuse_rnorm = fuse_rnorm
         self._keep: List[object] = []            # device tensors / ctypes structs referenced by raw pointer
         self.ops: List[Tuple[str, Callable[[int], int]]] = []
-        self.time_ops: List[Tuple[str, Callable[[int], int]]] = []
-        self.text_ops: List[Tuple[str, Callable[[int], int]]] = []
         self.taps: Dict[str, torch.Tensor] = {}  # named activations for per-layer parity tests
         self.op_meta: Dict[str, dict] = {}       # GEMM shape / byte counts per conv launch (profiling aid)
-        self.loops: Dict[tuple, dict] = {}       # cached sampling loops (tables + captured step graph), see diffusion.py
-        self._w = {k: v.detach() for k, v in weights.items()}
-        self._build()
 
     # ------------------------------------------------------------------ helpers
     def _dev(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
@@ -118,6 +106,37 @@ class UnetEngine:
 
     def _add(self, tag: str, fn: Callable[[int], int], into=None):
         (into if into is not None else self.ops).append((tag, fn))
+
+
+    def _run(self, ops, stream: Optional[int] = None):
+        if stream is not None:
+            s = stream
+        else:
+            s = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+        for tag, fn in ops:
+            rc = fn(s)
+            if rc != 0:
+                _lib.check(rc, tag)
+
+
+
+class UnetEngine(PlanOps):
+    def __init__(self, spec: UnetSpec, weights: Dict[str, torch.Tensor], batch: int, height: int, width: int,
+                 device: torch.device, time_rows: int = 1, text_tokens: int = 0, fuse_rnorm: bool = True, lib=None):
+        """`time_rows` is 1 when every sample shares the timestep (sampling loops, dd:641,682) or `batch`."""
+        assert height % spec.downsample_factor == 0 and width % spec.downsample_factor == 0, \
+            f"your input dimensions {(height, width)} need to be divisible by {spec.downsample_factor}, given the unet"
+        assert time_rows in (1, batch)
+        self.spec, self.B, self.H, self.W = spec, batch, height, width
+        self._init_plan(device, lib)
+        self.time_rows = time_rows
+        self.text_tokens = text_tokens
+        self.fuse_rnorm = fuse_rnorm
+        self.time_ops: List[Tuple[str, Callable[[int], int]]] = []
+        self.text_ops: List[Tuple[str, Callable[[int], int]]] = []
+        self.loops: Dict[tuple, dict] = {}       # cached sampling loops (tables + captured step graph), see diffusion.py
+        self._w = {k: v.detach() for k, v in weights.items()}
+        self._build()
 
     # ------------------------------------------------------------------ plan
     def _build(self):
@@ -415,16 +434,6 @@ class UnetEngine:
         return table
 
     # ------------------------------------------------------------------ execution
-    def _run(self, ops, stream: Optional[int] = None):
-        if stream is not None:
-            s = stream
-        else:
-            s = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
-        for tag, fn in ops:
-            rc = fn(s)
-            if rc != 0:
-                _lib.check(rc, tag)
-
     def run_time_path(self, stream=None):
         self._run(self.time_ops, stream)
 

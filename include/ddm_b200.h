@@ -123,6 +123,12 @@ int ddm_rmsnorm_act(const void* x_bf16, const float* norm_g, const float* scale_
                     long long rows_per_batch, int act, const void* residual_bf16, void* out_bf16, long long rows, int C,
                     void* stream);
 
+/* GroupNorm (+ swish) of the VAE decoder (latent-diffusion/ldm/modules/diffusionmodules/model.py:55-56 Normalize =
+ * GroupNorm(32, C, eps=1e-6), and the x*sigmoid(x) behind it at :118-119,127-128,573-574): x, out bf16 [B, HW, C]
+ * channels-last, `groups` groups of C/groups consecutive channels, statistics over one image; act 0 = none, 1 = swish. */
+int ddm_groupnorm_act(const void* x_bf16, const float* gamma, const float* beta, void* out_bf16, int B, int HW, int C, int groups, float eps,
+                      int act, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * K6: linear attention core (dd:178-192).  qkv: bf16 [B, n, 3*heads*d] (q | k | v, head-major channels),
  * mem_kv: fp32 [2][heads][d][n_mem] (dd:163); out: bf16 [B, n, heads*d].  d must be 16, 32 or 64.
@@ -163,6 +169,8 @@ int ddm_debug_linattn_trace(long long* host_triples, int cap);
  * K7/K8: softmax attention (dd:220-228 + at:109-124; tc:66-77).  q: bf16 rows [B*nq] with row stride ldq, head h at
  * column h*d; k, v likewise over [B*nk] rows; optional learned memory rows mem_k/mem_v fp32 [heads][n_mem][d] are
  * prepended to the keys/values (dd:223-224).  out: bf16 [B*nq][heads*d].  scale = d^-0.5.
+ * d = 32 / 64 / 128 run on tcgen05 (S = Q K^T and O = P V in TMEM, attention_tc.cu); this also serves the single-head
+ * AttnBlock of the VAE decoder (ldm/modules/diffusionmodules/model.py:190-215, d = C).  d = 16 uses CUDA cores.
  * ------------------------------------------------------------------------------------------------------------- */
 int ddm_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const float* mem_k,
                   const float* mem_v, int n_mem, void* out_bf16, int B, int nq, int nk, int heads, int d, void* stream);

@@ -22,4 +22,5 @@ from .sampler_ref import (  # noqa: F401
     model_predictions, ddim_update, ddpm_update, q_sample, interpolate, ddpm_update_learned, p_sample_loop_learned,
     ddim_sample_guided,
 )
+from .vae_ref import vae_decode, decoder_forward  # noqa: F401
 from .weights import synth_state_dict  # noqa: F401

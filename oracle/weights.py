@@ -31,6 +31,8 @@ def synth_tensor(name: str, shape: Sequence[int], seed: int = 0) -> torch.Tensor
         return torch.randn(shape, generator=g)
     if leaf == "bias":
         return 0.05 * torch.randn(shape, generator=g)
+    if leaf == "weight" and len(shape) == 1:          # GroupNorm gains (VAE decoder): near 1 but not all ones
+        return 1.0 + 0.1 * torch.randn(shape, generator=g)
     if leaf == "weight" and len(shape) >= 2:          # conv / linear: variance 1/fan_in
         fan_in = 1
         for s in shape[1:]:

@@ -154,6 +154,16 @@ class FakeLib:
         self.view(out, (rows, C_), bf).copy_(y.to(bf))
         return 0
 
+    def ddm_groupnorm_act(self, x, gamma, beta, out, B, HW, C_, groups, eps, act, stream):
+        self.calls += 1
+        bf, f32 = torch.bfloat16, torch.float32
+        xv = self.view(x, (B, HW, C_), bf).float().permute(0, 2, 1)                       # [B, C, HW]
+        y = torch.nn.functional.group_norm(xv, groups, self.view(gamma, (C_,), f32), self.view(beta, (C_,), f32), eps=eps)
+        if act == 1:
+            y = y * torch.sigmoid(y)
+        self.view(out, (B, HW, C_), bf).copy_(y.permute(0, 2, 1).to(bf))
+        return 0
+
     def ddm_linear_attention(self, qkv, mem_kv, out, B, n, heads, d, n_mem, stream):
         self.calls += 1
         bf = torch.bfloat16

@@ -62,5 +62,44 @@ def main():
     save("ddim_guided_noguide_S4", y=y, x_T=cap.draws[0], noises=torch.stack(cap.draws[1:]))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# VAE decode: the reference's Decoder + post_quant_conv, imported unmodified
+# (ldm/modules/diffusionmodules/model.py needs only torch / numpy / einops; VQModel itself needs pytorch_lightning + taming,
+# which are absent -- its decode() is exactly `decoder(post_quant_conv(quant))`, autoencoder.py:113-116).
+@torch.inference_mode()
+def vae_fixtures():
+    import json
+    sys.path.insert(0, "/root/reference/latent-diffusion")
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference prints shapes while constructing
+        from ldm.modules.diffusionmodules.model import Decoder
+        cfgs = {
+            # the reference's own first-stage config (latent-diffusion/train/configs/VAE_cifar.yaml): 3x16x16 latents -> 3x32x32
+            "vae_decode_cifar": (dict(double_z=False, z_channels=3, resolution=32, in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2],
+                                      num_res_blocks=2, attn_resolutions=[], dropout=0.0), 3, (2, 3, 16, 16)),
+            # attention inside an up level and three levels (exercises AttnBlock at 64 channels and two upsamplings)
+            "vae_decode_attn": (dict(double_z=False, z_channels=4, resolution=32, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2],
+                                     num_res_blocks=1, attn_resolutions=[16], dropout=0.0), 4, (1, 4, 8, 8)),
+        }
+        manifest = {}
+        for name, (ddconfig, embed_dim, zshape) in cfgs.items():
+            dec = Decoder(**ddconfig).eval()
+            pq = torch.nn.Conv2d(embed_dim, ddconfig["z_channels"], 1).eval()
+            from oracle.weights import synth_state_dict
+            shapes = {"decoder." + k: tuple(v.shape) for k, v in dec.state_dict().items()}
+            shapes.update({"post_quant_conv." + k: tuple(v.shape) for k, v in pq.state_dict().items()})
+            sd = synth_state_dict(shapes, 31)
+            dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+            pq.load_state_dict({k[len("post_quant_conv."):]: v for k, v in sd.items() if k.startswith("post_quant_conv.")}, strict=True)
+            z = rnd(zshape, 300)
+            y = dec(pq(z))
+            manifest[name] = dict(ddconfig=ddconfig, embed_dim=embed_dim, shapes={k: list(s) for k, s in shapes.items()})
+            save(name, z=z, y=y)
+    with open(os.path.join(HERE, "manifest_vae.json"), "w") as f:
+        json.dump(manifest, f, indent=0, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "vae" not in sys.argv[1:]:
+        main()
+    vae_fixtures()

@@ -157,3 +157,15 @@ def test_ddim_guided(golden):
     g = golden("ddim_guided_noguide_S4")  # no guide, clip_denoised=False: raw eps, unclamped x0
     y = ddim_sample_guided(_model(), make_schedule(1000), g["x_T"], 4, eta=0.5, clip_denoised=False, noises=list(g["noises"]))
     _close(y, g["y"], 1e-3)
+
+
+@pytest.mark.parametrize("name", ["vae_decode_cifar", "vae_decode_attn"])
+@torch.inference_mode()
+def test_vae_decode_matches_reference(name, golden):
+    """oracle/vae_ref.py against the reference's Decoder + post_quant_conv (tests/golden/make_golden_r2.py vae_fixtures)."""
+    from oracle import vae_decode
+    with open(os.path.join(GOLDEN, "manifest_vae.json")) as f:
+        m = json.load(f)[name]
+    sd = synth_state_dict({k: tuple(v) for k, v in m["shapes"].items()}, 31)
+    g = golden(name)
+    _close(vae_decode(sd, g["z"]), g["y"])

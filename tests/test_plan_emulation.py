@@ -97,3 +97,28 @@ def test_text_concat():
 def test_full_attention_everywhere_and_odd_sizes():
     eng, ref, _ = run_case(ddm.Unet(dim=32, dim_mults=(1, 2), full_attn=(True, True)), 10, g((1, 3, 8, 24), 9), torch.tensor([42]))
     assert rel_l2(eng.out, ref) < 2e-2
+
+
+@pytest.mark.parametrize("name", ["vae_decode_cifar", "vae_decode_attn"])
+def test_vae_decode_plan(name):
+    """The real VaeDecodeEngine plan (post_quant as a 1x1 stem, padded conv_in, GroupNorm pre-passes, fused residuals, stacked
+    q|k|v GEMM + single-head attention, sub-pixel upsampling) through the C-ABI stand-in, against the fp32 oracle."""
+    import numpy as np
+    from conftest import GOLDEN
+    from oracle import vae_decode
+    with open(os.path.join(GOLDEN, "manifest_vae.json")) as f:
+        m = json.load(f)[name]
+    vae = ddm.VQDecoder(ddconfig=m["ddconfig"], embed_dim=m["embed_dim"])
+    assert {k: list(v.shape) for k, v in vae.state_dict().items()} == m["shapes"]
+    sd = synth_state_dict({k: tuple(v) for k, v in m["shapes"].items()}, 31)
+    vae.load_state_dict(sd)
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        zin, want = torch.from_numpy(z["z"]), torch.from_numpy(z["y"])
+    lib = FakeLib()
+    eng = vae.engine(zin.shape[0], zin.shape[2], zin.shape[3], torch.device("cpu"), lib=lib)
+    lib.attach(eng)
+    eng.z.copy_(zin)
+    eng.run()
+    with torch.inference_mode():
+        ref = vae_decode(sd, zin)
+    assert rel_l2(eng.out, ref) < 2e-2 and rel_l2(eng.out, want) < 2e-2, (rel_l2(eng.out, ref), rel_l2(eng.out, want))
