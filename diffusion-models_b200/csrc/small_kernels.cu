@@ -259,11 +259,12 @@ rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 __global__ void __launch_bounds__(512)
 groupnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ out, int HW, int C, int G, float eps, int act) {
-    extern __shared__ float gsm[];            // [C] sum | [C] sum of squares -> reused as [C] scale | [C] shift ; then [G] mean | [G] rstd
-    float* ch_a = gsm;
-    float* ch_b = gsm + C;
+    extern __shared__ float gsm[];            // [C] sum | [C] sum of squares -> reused as [C] scale | [C] shift ; [G] mean | [G] rstd ;
+    float* ch_a = gsm;                        // then per-thread partial sums [512][16] (fixed-order reduction: bitwise repeatable
+    float* ch_b = gsm + C;                    // and independent of the batch, unlike shared-memory atomics)
     float* g_mean = gsm + 2 * C;
     float* g_rstd = g_mean + G;
+    float* part = g_rstd + G;
     const int tid = threadIdx.x;
     const __nv_bfloat16* xb = x + static_cast<long long>(blockIdx.x) * HW * C;
     __nv_bfloat16* ob = out + static_cast<long long>(blockIdx.x) * HW * C;
@@ -271,13 +272,11 @@ groupnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     const int rstep = blockDim.x / nvec;      // pixels in flight per sweep step
     const int v = tid % nvec, r0 = tid / nvec;
     const bool live = r0 < rstep;
-    for (int c = tid; c < 2 * C; c += blockDim.x) gsm[c] = 0.0f;
-    __syncthreads();
-    if (live) {
+    {
         float s[8], q[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] = 0.0f; q[j] = 0.0f; }
-        for (int row = r0; row < HW; row += rstep) {
+        for (int row = r0; live && row < HW; row += rstep) {
             const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(row) * C) + v);
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -288,7 +287,18 @@ groupnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(ch_a + v * 8 + j, s[j]); atomicAdd(ch_b + v * 8 + j, q[j]); }
+        for (int j = 0; j < 8; ++j) { part[tid * 16 + j] = s[j]; part[tid * 16 + 8 + j] = q[j]; }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {       // channel c = vector c / 8, element c % 8: the rstep pixel-lanes in order
+        float s = 0.0f, q = 0.0f;
+        for (int r = 0; r < rstep; ++r) {
+            const float* pp = part + ((r * nvec + (c >> 3)) * 16) + (c & 7);
+            s += pp[0];
+            q += pp[8];
+        }
+        ch_a[c] = s;
+        ch_b[c] = q;
     }
     __syncthreads();
     const int cg = C / G;
@@ -620,7 +630,7 @@ int launch_groupnorm_act(const void* x, const float* gamma, const float* beta, v
                          cudaStream_t s) {
     const int nvec = C / 8;
     if (C % 8 != 0 || nvec > 512 || G < 1 || G > 512 || C % G != 0) return -3;
-    const int smem = (2 * C + 2 * G) * 4;
+    const int smem = (2 * C + 2 * G + 512 * 16) * 4;
     if (smem > 48 * 1024) return -3;
     groupnorm_act_kernel<<<B, 512, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), HW,
                                               C, G, eps, act);
