@@ -101,7 +101,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if all(os.path.getmtime(d) <= lib_m for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    dbg = ["-DDDM_CONV_DEBUG_BUILD"] if os.environ.get("DDM_CONV_DEBUG_BUILD") else []     # in-kernel bisection / trace switches
+    cmd = [nvcc] + NVCC_FLAGS + dbg + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -17,6 +17,16 @@ struct alignas(8) ConvBarriers {
     int issued;                  // MMA issue token: number of pipeline stages whose MMAs have all been issued
 };
 
+// Profiling / bisection switches of DDM_CONV_DEBUG that act INSIDE the kernel (skip epilogue / MMA / A loads, event trace,
+// fence bisection) exist only in a build with -DDDM_CONV_DEBUG_BUILD: in the product build kDbg is 0, so every test below
+// is a compile-time false and neither the branches nor the trace stores are in the SASS.  (Mode selection on the host --
+// folding, epilogue groups, issuer modes -- keeps working either way.)
+#ifdef DDM_CONV_DEBUG_BUILD
+constexpr int kDbg = -1;
+#else
+constexpr int kDbg = 0;
+#endif
+
 // Device-side event trace for pipeline debugging (DDM_CONV_DEBUG & 128): CTA 0 records (role, event, tile, clock).
 constexpr int kTraceRoles = 5, kTraceCap = 1024;      // per-role rings, no atomics: stores are fire-and-forget
 __device__ long long g_trace[kTraceRoles * kTraceCap * 2];
@@ -137,9 +147,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t tmem_base = bars->tmem_base;
 
     const int chunks_per_tap = p.chunks0 + p.chunks1;
-    const bool tr = (p.debug & 128) && blockIdx.x == 0;
-    const bool tr_iss = (p.debug & (128 | 4096)) && blockIdx.x == 0;      // 4096: only the issuers' token/issued events
-    const bool tr_tile = (p.debug & (128 | 256)) && blockIdx.x == 0;     // 256: per-tile events only (unperturbed timing)
+    const bool tr = ((p.debug & kDbg) & 128) && blockIdx.x == 0;
+    const bool tr_iss = ((p.debug & kDbg) & (128 | 4096)) && blockIdx.x == 0;      // 4096: only the issuers' token/issued events
+    const bool tr_tile = ((p.debug & kDbg) & (128 | 256)) && blockIdx.x == 0;     // 256: per-tile events only (unperturbed timing)
     int trn = 0;
     // Tile sequence of this CTA.  Without clusters: tiles blockIdx.x, +gridDim.x, ...  With 2-CTA clusters (weights
     // multicast): cluster c takes pair sequence c, c + n_clusters, ...; the pair's two M tiles go to the two CTAs and
@@ -203,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         if (elect_one()) {
                             trace_ev(tr, 0, 0, q, trn);
                             uint8_t* a_dst = smem + (base + stage) * stage_bytes;
-                            const bool skip_a = (p.debug & 4) != 0;      // profiling: no A traffic
+                            const bool skip_a = ((p.debug & kDbg) & 4) != 0;      // profiling: no A traffic
                             const uint32_t tx_bytes = static_cast<uint32_t>(skip_a ? stage_bytes - plan.a_bytes : stage_bytes);
                             mbar_arrive_expect_tx(&bars->full[base + stage], tx_bytes);
                             if (skip_a) {
@@ -261,7 +271,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t wres_lo = smem_u32(wres) >> 4;
             const int n_dy = p.n_dy;
             const bool resident = p.b_resident != 0;
-            const bool do_mma = (p.debug & 2) == 0;
+            const bool do_mma = ((p.debug & kDbg) & 2) == 0;
             volatile int* issued = &bars->issued;
             int stage = 0;
             uint32_t phase = 0;
@@ -334,7 +344,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 }
                             }
                             trace_ev(tr_iss, 1 + me, 3, g, trn);
-                            if (dual) { if (!(p.debug & 8192)) __threadfence_block(); *issued = g + 1; }     // pass the token
+                            if (dual) { if (!((p.debug & kDbg) & 8192)) __threadfence_block(); *issued = g + 1; }     // pass the token
                             if (cl == 2) umma_commit_mc(&bars->empty[ring_base + stage], 0x3); else umma_commit(&bars->empty[ring_base + stage]);
                             trace_ev(tr, 1 + me, 4, g, trn);
                             }
@@ -384,7 +394,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint32_t res_phase = 0;
         const bool want_rs = p.row_scale != nullptr, want_rn = p.rnorm_out != nullptr;
         const bool need_geo = leader_warp || (res_smem && !res_tma) || want_rs || want_rn;   // who needs the tile's coordinates
-        const bool skip = (p.debug & 1) != 0;   // profiling: no epilogue math / stores
+        const bool skip = ((p.debug & kDbg) & 1) != 0;   // profiling: no epilogue math / stores
         const int stg_bytes = kTileM * p.block_n * 2;
         const int tiles_xy = p.tiles_x * p.tiles_y;
         // offset of this thread's pixel inside a (full) tile of the [B,H,W] grid, for row_scale / rnorm_out
@@ -450,7 +460,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         float* const gred_b = red_b + grp * kGParts * kTileM;
         // measured: pays for the dx-folded kernels (-6 %), neutral or worse elsewhere (with two accumulator stages it
         // serialises the next tile's MMA with this tile's store)
-        const bool merge_acc = FOLD != 0 && p.acc_stages == 4 && (p.debug & 1048576) == 0;
+        const bool merge_acc = FOLD != 0 && p.acc_stages == 4 && ((p.debug & kDbg) & 1048576) == 0;
         bool acc_ready = false;
         int n_tile, m_tile;
         for (int q = grp; seq_tile(q, n_tile, m_tile); q += GROUPS) {
@@ -800,7 +810,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (lane == 0) mbar_wait(&bars->acc_full[acc], acc_phase);   // one polling lane per warp: 512 pollers saturate the smem pipe
             __syncwarp();
             tc_fence_after();
-            if (p.debug & 1) {                // profiling: epilogue does nothing but release the accumulator
+            if ((p.debug & kDbg) & 1) {                // profiling: epilogue does nothing but release the accumulator
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);

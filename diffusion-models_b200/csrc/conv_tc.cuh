@@ -66,7 +66,8 @@ struct ConvParams {
     int pairs;                   // ceil(m_tiles / 2) when cluster == 2
     int issue_mode;              // 0: one MMA issuer thread; 1: two issuers alternating pipeline stages in token order;
                                  // 2: two issuers alternating tiles, each with its own half of the smem ring
-    int debug;                   // profiling / bisection only (env DDM_CONV_DEBUG, read once in ddm_init); bits:
+    int debug;                   // profiling / bisection only (env DDM_CONV_DEBUG, read once in ddm_init; the bits that act inside
+                                 // the kernel -- 1 2 4 128 256 4096 8192 1048576 -- need a -DDDM_CONV_DEBUG_BUILD build); bits:
                                  //   1 skip epilogue work      2 skip MMA issue        4 skip A loads
                                  //   8 generic epilogue only   32 single MMA issuer    64 2-CTA weight multicast ON
                                  //   128 device-side event trace of CTA 0 (ddm_debug_conv_trace)   256 per-tile events only
