@@ -21,6 +21,7 @@ from .engine import UnetEngine
 ModelPrediction = namedtuple("ModelPrediction", ["pred_noise", "pred_x_start"])
 
 _OBJECTIVES = {"pred_noise": 0, "pred_x0": 1, "pred_v": 2}
+MAX_GRAPH_STEPS = 250       # steps captured into one CUDA graph (x ~105 kernel nodes each)
 
 
 def _p(t):
@@ -353,19 +354,26 @@ class DenoisingDiffusion(nn.Module):
                 counter.copy_(torch.tensor([0, loop["epoch"]], dtype=torch.int32))
                 if eng.x_self_cond is not None:
                     eng.x_self_cond.zero_()
+                # The WHOLE step loop is one CUDA graph: `chunk` steps are captured back to back (the device-side step
+                # counter makes every step of the capture pick its own table rows), so a sampling call is S / chunk host
+                # launches -- one for S <= MAX_GRAPH_STEPS (DDIM-50 / -100 / -250).  Longer loops (the 1000-step ancestral
+                # sampler) replay a chunk that divides S, keeping the instantiated graph at a few thousand kernel nodes.
+                chunk = S if S <= MAX_GRAPH_STEPS else max(d for d in range(1, MAX_GRAPH_STEPS + 1) if S % d == 0)
                 graph = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize(dev)
                 n0 = _lib.launch_count()
                 with torch.cuda.graph(graph):
-                    step_ops(torch.cuda.current_stream(dev).cuda_stream)
-                loop["per_step"] = _lib.launch_count() - n0
-                loop["graph"] = graph
+                    for _ in range(chunk):
+                        step_ops(torch.cuda.current_stream(dev).cuda_stream)
+                loop["per_step"] = (_lib.launch_count() - n0) // chunk
+                loop["graph"], loop["chunk"] = graph, chunk
                 loop["keep"] = step_noise                         # raw pointers baked into the graph
             eng.x.copy_(x_T)
             graph = loop["graph"]
-            for _ in range(S):
+            for _ in range(S // loop["chunk"]):
                 graph.replay()
             self._last_graph_launches = loop["per_step"] * S      # kernels launched by replays (not via the C-ABI counter)
+            self._last_host_launches = S // loop["chunk"]
         ret = eng.x.clone() if imgs is None else torch.stack(imgs, dim=1)
         out = torch.empty_like(ret)
         _lib.check(lib.ddm_finalize(ret.data_ptr(), out.data_ptr(), 1 if (self._auto_normalize and not raw) else 0, ret.numel(),

@@ -151,6 +151,18 @@ def test_ddim_teacher_forced_and_free_running(golden):
     # sample() dispatches to DDIM when sampling_timesteps < timesteps (dd:779-783); graph replay == eager launches
     y_eager = d.ddim_sample((2, 3, 32, 32), noise=g["x_T"].cuda(), use_graph=False)
     assert torch.equal(y, y_eager)
+    assert d._last_host_launches == 1            # the whole 5-step loop is ONE captured CUDA graph (north_star 4)
+    # loops longer than MAX_GRAPH_STEPS replay a chunk that divides the step count: same bits
+    from diffusion_models_b200 import diffusion as dmod
+    old = dmod.MAX_GRAPH_STEPS
+    try:
+        dmod.MAX_GRAPH_STEPS = 2
+        d2 = _diffusion(model, sampling_timesteps=6)
+        y6 = d2.ddim_sample((2, 3, 32, 32), noise=g["x_T"].cuda())
+        assert d2._last_host_launches == 3
+        assert torch.equal(y6, d2.ddim_sample((2, 3, 32, 32), noise=g["x_T"].cuda(), use_graph=False))
+    finally:
+        dmod.MAX_GRAPH_STEPS = old
 
 
 def test_ddim_eta1_injected_noise_all_timesteps(golden):
