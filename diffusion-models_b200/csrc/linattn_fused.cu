@@ -48,8 +48,10 @@ constexpr int kGroupThreads = kEpiThreads / 2; // two epilogue groups of 8 warps
 //           (and in pass 1 the TMA warp) arrived too -> two ids (buffer parity) suffice;
 //   ydone : consumed by the TMA warp alone; with a ring of kNbuf = 4 tiles, tile t + 4 can only be loaded after the TMA warp
 //           stored tile t, i.e. passed ydone(t) -> four ids (t & 3) can never be over-run.
-constexpr int kBarEpi = 1, kBarEdone = 3, kBarYdone = 5, kBarCdone = 9, kBarMtdone = 10, kBarAll = 11;
-constexpr int kPass1Edone = kGroupThreads + 96, kPass2Edone = kGroupThreads + 64;    // group + (K, Cx, TMA) / + (K, Cx)
+//   afree : the group's next arrival needs the accumulator that K fills after passing this one -> two ids.
+constexpr int kBarEpi = 1, kBarEdone = 3, kBarYdone = 5, kBarCdone = 9, kBarMtdone = 10, kBarAll = 11, kBarAfree = 12;
+constexpr int kPass1Edone = kGroupThreads + 64, kPass2Edone = kGroupThreads + 32;    // group + (Cx, TMA) / + Cx
+constexpr int kAfree = kGroupThreads + 32;                                            // group + K
 
 struct LaParams {
     const float* bias_out;   // [C]
@@ -323,7 +325,8 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 TR(10, 0);
                 issue_kv(G, 1);
                 for (int j = 0; j < J; ++j) {
-                    wait_edone(j & 1, kPass1Edone);              // accumulator j & 1 read out by its group
+                    named_bar_sync(kBarAfree + (j & 1), kAfree);   // accumulator j & 1 read out by its group (mid-epilogue)
+                    tc_fence_after();
                     TR(11, j);
                     if (j + 2 < J) {
                         const int gt = G + ((j + 2) >> 1);
@@ -339,7 +342,8 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 issue_q(G2, 0);
                 if (T > 1) { wait_x(G2 + 1); issue_q(G2 + 1, 1); }
                 for (int t = 0; t < T; ++t) {
-                    wait_edone(t & 1, kPass2Edone);              // Q accumulator t & 1 read out
+                    named_bar_sync(kBarAfree + (t & 1), kAfree);   // Q accumulator t & 1 read out (mid-epilogue)
+                    tc_fence_after();
                     TR(21, t);
                     if (t + 2 < T) { wait_x(G2 + t + 2); issue_q(G2 + t + 2, t + 2); }
                 }
@@ -493,6 +497,10 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                             bl[4 * i] = b4.x; bl[4 * i + 1] = b4.y; bl[4 * i + 2] = b4.z; bl[4 * i + 3] = b4.w;
                         }
                         tmem_ld_wait();
+                        if (hh == 1) {      // the accumulator is in registers: K may refill it while the rest of the math runs
+                            tc_fence_before();
+                            named_bar_arrive(kBarAfree + grp, kAfree);
+                        }
                         uint32_t pw[8], vw[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -604,6 +612,10 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                         uint32_t qr[32];
                         tmem_ld32(t_lane + static_cast<uint32_t>(grp * 128 + half * 64 + hh * 32), qr);
                         tmem_ld_wait();
+                        if (hh == 1) {      // Q accumulator fully read: K may issue the next Q tile of this group
+                            tc_fence_before();
+                            named_bar_arrive(kBarAfree + grp, kAfree);
+                        }
                         float m0 = fmaxf(__uint_as_float(qr[0]), __uint_as_float(qr[1])), m1 = fmaxf(__uint_as_float(qr[2]), __uint_as_float(qr[3]));
                         float m2 = fmaxf(__uint_as_float(qr[4]), __uint_as_float(qr[5])), m3 = fmaxf(__uint_as_float(qr[6]), __uint_as_float(qr[7]));
 #pragma unroll
