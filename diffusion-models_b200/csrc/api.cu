@@ -164,6 +164,17 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     const bool qkv_three_tiles = a->N_pad == 384 && a->K_pad == 64 && a->norm_g == nullptr && a->rnorm_out == nullptr &&
                                  a->residual == nullptr && !(g_conv_debug & 16777216);
     if (qkv_three_tiles) { p.n_tiles = 3; p.block_n = 128; }
+    // Small M (the 4x4 / 8x8 levels at small per-GPU batches): with 256-wide N tiles a 512-channel layer at M = 2048 is 32 tiles
+    // for 148 SMs.  Narrower N tiles multiply the tile count at the same total weight traffic (each tile streams its own
+    // slice of W; only the small A operand is re-read, from L2): halve block_n while that still leaves most SMs idle.
+    // Not with a fused row norm (one tile must own the whole output row).  DDM_CONV_DEBUG & 33554432 disables it.
+    if (a->norm_g == nullptr && a->rnorm_out == nullptr && !qkv_three_tiles && !(g_conv_debug & 33554432)) {
+        while (p.m_tiles * p.n_tiles * 2 <= g_num_sms && p.block_n >= 128 && (p.block_n % 128) == 0 &&      // tiles stay 64-channel
+               (a->N_pad % (p.block_n / 2)) == 0) {                                                         // groups (TMA store)
+            p.block_n /= 2;
+            p.n_tiles = a->N_pad / p.block_n;
+        }
+    }
     p.total_tiles = p.m_tiles * p.n_tiles;
     p.N = a->N;
     if (a->norm_g != nullptr && p.n_tiles != 1) return DDM_E_UNSUPPORTED;

@@ -448,10 +448,13 @@ def test_vae_decode_vs_reference_golden(name, golden):
     y = vae.decode(g["z"].cuda())
     assert y.shape == g["y"].shape and y.dtype == torch.float32
     assert rel_l2(y, g["y"]) < EPS_TOL, rel_l2(y, g["y"])
-    # batch invariance at a BASELINE-sized batch (no batch statistics: GroupNorm is per image)
+    # batch invariance at a BASELINE-sized batch (no batch statistics: GroupNorm is per image).  Not bitwise: at B = 4 the conv
+    # kernel picks narrower N tiles to fill the SMs (api.cu), the tensor core then rounds a few fp32 sums differently, and the
+    # bf16 activations downstream flip by an ulp here and there -- well inside the parity tolerance.
     zb = torch.randn((256,) + tuple(g["z"].shape[1:]), generator=torch.Generator().manual_seed(7)).cuda()
     yb = vae.decode(zb)
-    assert torch.isfinite(yb).all() and rel_l2(vae.decode(zb[100:104]), yb[100:104]) < 1e-6
+    assert torch.isfinite(yb).all() and rel_l2(vae.decode(zb[100:104]), yb[100:104]) < EPS_TOL
+    assert torch.equal(vae.decode(zb), yb)           # the same launch configuration is bitwise repeatable
 
 
 def test_latent_diffusion_sample_end_to_end_on_kernels():
