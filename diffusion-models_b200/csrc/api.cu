@@ -16,7 +16,7 @@
 namespace ddm {
 void launch_linattn_fused(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmWqkv, const CUtensorMap& tmWout,
                           const float* bias_out, const float* g_out, const float* mem_kv, const float* k_shift, int B, int n, int C,
-                          int n_mem, int num_sms, int trace, cudaStream_t s);
+                          int n_mem, int num_sms, int trace, bool pdl, cudaStream_t s);
 int linattn_trace_read(long long* host, int cap);
 int attention_tc_prepare_attributes();
 bool attention_tc_supported(int d, int n_mem);
@@ -32,6 +32,7 @@ bool g_ready = false;
 int g_conv_debug = 0;
 int g_laf_trace = 0;
 bool g_tc_attention = true;
+bool g_pdl = true;             // programmatic dependent launch of the big kernels (DDM_NO_PDL=1 disables, for A/B timing)
 std::atomic<long long> g_launches{0};
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -118,7 +119,8 @@ static int init_on_current_device(int device) {
     if (r != 0) return r;
     r = ddm::attention_tc_prepare_attributes();
     if (r != 0) return r;
-    if (std::getenv("DDM_NO_TC_ATTENTION")) g_tc_attention = false;      // A/B timing against the CUDA-core kernel
+    if (std::getenv("DDM_NO_TC_ATTENTION")) g_tc_attention = false;
+    if (std::getenv("DDM_NO_PDL")) g_pdl = false;      // A/B timing against the CUDA-core kernel
     if (const char* t = std::getenv("DDM_LAF_TRACE")) g_laf_trace = std::atoi(t);       // scripts/laf_trace.py
     if (const char* dbg = std::getenv("DDM_CONV_DEBUG")) g_conv_debug = std::atoi(dbg);   // bottleneck bisection, see conv_tc.cuh
     g_ready = true;
@@ -393,7 +395,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             p.res_tma = 1;
         }
     }
-    ddm::launch_conv(tmA0, tmA1, tmW, tmOut, tmRes, p, g_num_sms, as_stream(stream));
+    ddm::launch_conv(tmA0, tmA1, tmW, tmOut, tmRes, p, g_num_sms, as_stream(stream), g_pdl);
     return finish(1);
 }
 
@@ -515,7 +517,7 @@ int ddm_linear_attention_block(const ddm_linattn_block_args* a, void* stream) {
         if (r != 0) return r;
     }
     ddm::launch_linattn_fused(tmX, tmY, tmWqkv, tmWout, a->bias_out, a->g_out, a->mem_kv, a->k_shift, a->B, a->n, a->C, a->n_mem,
-                              g_num_sms, g_laf_trace, as_stream(stream));
+                              g_num_sms, g_laf_trace, g_pdl, as_stream(stream));
     return finish(1);
 }
 

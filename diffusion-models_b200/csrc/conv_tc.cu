@@ -102,6 +102,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool ss_batched = (p.scale_shift != nullptr) && (p.ss_stride != 0);
     const bool affine = (p.norm_g != nullptr) || ss_uniform;
 
+    griddep_launch();                                       // the next kernel of the stream may start its own prologue
     const uint32_t cl_count = p.cluster == 2 ? 2u : 1u;     // a stage is released by the issuers of every CTA of the cluster
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
@@ -121,11 +122,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         prefetch_tmap(&tmW);
         prefetch_tmap(&tmOut);
         prefetch_tmap(&tmRes);
+        if (p.b_resident) {       // the weights of this (single) N tile are loaded once per CTA; they do not depend on the
+                                  // previous kernel, so the load is in flight before griddep_wait()
+            const SmemPlan pl = make_plan(p, p.num_stages);
+            const int cpt = p.chunks0 + p.chunks1;
+            mbar_arrive_expect_tx(&bars->w_full, static_cast<uint32_t>(p.k_chunks * pl.b_chunk_bytes));
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                int slot = kc;
+                if constexpr (FOLD) {       // stacked layout: block (dy, chunk) = [dx=-1 | dx=0 | dx=+1] x 64 rows
+                    const int tap = kc / cpt, c = kc - tap * cpt;
+                    slot = (p.fold_dyi[tap] * cpt + c) * 3 + p.fold_dxi[tap];
+                }
+                tma_load_2d(smem + pl.wres_off + slot * pl.b_chunk_bytes, &tmW, &bars->w_full, kc * kChunkK, 0);
+            }
+        }
     }
     if (warp == 1) {
         tmem_alloc(&bars->tmem_base, static_cast<uint32_t>(p.tmem_cols));
         tmem_relinquish();
     }
+    griddep_wait();               // everything below reads what earlier kernels of the stream wrote (activations, scale/shift row)
     // per-column epilogue vectors: v = acc*rs + bias ; [v *= rinv] ; v = v*mul + add
     for (int n = threadIdx.x; n < p.n_pad; n += blockDim.x) {
         const bool in = n < p.N;
@@ -178,17 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         {
-            if (p.b_resident && elect_one()) {       // the weights of this (single) N tile are loaded once per CTA
-                mbar_arrive_expect_tx(&bars->w_full, static_cast<uint32_t>(p.k_chunks * plan.b_chunk_bytes));
-                for (int kc = 0; kc < p.k_chunks; ++kc) {
-                    int slot = kc;
-                    if constexpr (FOLD) {       // stacked layout: block (dy, chunk) = [dx=-1 | dx=0 | dx=+1] x 64 rows
-                        const int tap = kc / chunks_per_tap, c = kc - tap * chunks_per_tap;
-                        slot = (p.fold_dyi[tap] * chunks_per_tap + c) * 3 + p.fold_dxi[tap];
-                    }
-                    tma_load_2d(wres + slot * plan.b_chunk_bytes, &tmW, &bars->w_full, kc * kChunkK, 0);
-                }
-            }
+            // (the resident weights were requested by thread 0 in the prologue, ahead of griddep_wait)
             // issue_mode 2 splits the ring in two halves, one per issuer thread (tile parity): every mbarrier then has
             // a single consumer that visits it in lap order, which parity-only waits require.
             const bool split = p.issue_mode == 2;
@@ -1051,7 +1057,7 @@ int conv_prepare_attributes() {
 }
 
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                 const CUtensorMap& tmRes, const ConvParams& p, int num_sms, cudaStream_t stream) {
+                 const CUtensorMap& tmRes, const ConvParams& p, int num_sms, cudaStream_t stream, bool pdl) {
     int stages = 0;
     const int smem = conv_smem_plan(p, &stages);
     int grid;
@@ -1067,13 +1073,15 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
     cfg.blockDim = dim3(96 + 32 * 16);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = p.cluster == 2 ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // programmatic dependent launch, see ptx.cuh
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 2 : 1;
     if (p.epi_groups == 4 && p.fold == 2) {
         cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 4>, tmA0, tmA1, tmW, tmOut, tmRes, p);
     } else if (p.epi_groups == 4) {

@@ -95,7 +95,7 @@ struct ConvParams {
 };
 
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                 const CUtensorMap& tmRes, const ConvParams& p, int num_sms, cudaStream_t stream);
+                 const CUtensorMap& tmRes, const ConvParams& p, int num_sms, cudaStream_t stream, bool pdl);
 // shared-memory plan: returns total dynamic bytes and the stage count that fits (0 stages = does not fit)
 int conv_smem_plan(const ConvParams& p, int* num_stages);
 int conv_prepare_attributes();

@@ -148,6 +148,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int n_img = (p.B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const int total_tiles = n_img * 2 * T;
 
+    griddep_launch();          // programmatic dependent launch (ptx.cuh): the next kernel may begin its prologue
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(&bars->xfull[i], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->accfull[i], 1); mbar_init(&bars->pvdone[i], 1); mbar_init(&bars->yfull[i], 1); }
@@ -255,6 +256,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
             __syncwarp();
             load_wout();
+            griddep_wait();        // the weights above are constants; x is the previous kernel's output
             pump();
             int G = 0;
             for (int it = 0; it < n_img; ++it, G += 2 * T) {
@@ -739,13 +741,23 @@ bool linattn_fused_supported(int C, int n, int heads, int d, int n_mem) {
 
 void launch_linattn_fused(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmWqkv, const CUtensorMap& tmWout,
                           const float* bias_out, const float* g_out, const float* mem_kv, const float* k_shift, int B, int n, int C,
-                          int n_mem, int num_sms, int trace, cudaStream_t s) {
+                          int n_mem, int num_sms, int trace, bool pdl, cudaStream_t s) {
     LaParams p;
     p.bias_out = bias_out; p.g_out = g_out; p.mem_kv = mem_kv; p.k_shift = k_shift;
     p.B = B; p.n = n; p.n_mem = n_mem;
     p.trace = trace;
     const int grid = B < num_sms ? B : num_sms;
-    linattn_fused_kernel<64><<<grid, kThreads, LaSmem<64>::kTotal + 1024, s>>>(tmX, tmY, tmWqkv, tmWout, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = LaSmem<64>::kTotal + 1024;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, linattn_fused_kernel<64>, tmX, tmY, tmWqkv, tmWout, p);
 }
 
 }  // namespace ddm

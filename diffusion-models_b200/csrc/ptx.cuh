@@ -20,6 +20,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running: griddep_launch() (early in the predecessor) lets the dependent's CTAs be scheduled as SMs free up, and the
+// dependent runs everything that does not touch the predecessor's results -- barrier init, TMEM allocation, tensor-map
+// prefetch, the TMA loads of its (constant) weights -- before griddep_wait(), which returns once the predecessor grid has
+// completed and its writes are visible.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
