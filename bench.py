@@ -264,7 +264,7 @@ def run_ours(args):
         ms = timed(sample_resident, args.steps)
     launches_api = ddm._lib.launch_count() - l0
     graph_nodes = getattr(diff, "_last_graph_launches", 0)
-    gpu_launches = launches_api + args.steps * graph_nodes
+    gpu_launches = (launches_api + args.steps * graph_nodes) * world          # whole job: every rank launches the same list
     sample_e2e()
     ms_e2e = timed(sample_e2e, args.steps)
 

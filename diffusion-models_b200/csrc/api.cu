@@ -9,6 +9,8 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "conv_tc.cuh"
 #include "kernels.cuh"
@@ -36,6 +38,19 @@ bool g_pdl = true;             // programmatic dependent launch of the big kerne
 std::atomic<long long> g_launches{0};
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ddm_conv2d plans (tile / slab / epilogue configuration + the five encoded tensor maps) are pure functions of the argument
+// struct: callers that keep their ddm_conv_args alive and unchanged (the engine does, one per layer) get them from this
+// cache instead of paying five cuTensorMapEncodeTiled driver calls per launch (~100 launches per eager U-Net forward).
+// Keyed by the struct's address, validated by comparing its bytes; bounded.
+struct ConvPlan {
+    ddm_conv_args args;
+    ddm::ConvParams p;
+    CUtensorMap tmA0, tmA1, tmW, tmOut, tmRes;
+};
+std::unordered_map<const ddm_conv_args*, ConvPlan> g_plans;
+std::mutex g_plans_mu;
+constexpr size_t kMaxPlans = 8192;
 inline int finish(int launches) {
     g_launches.fetch_add(launches, std::memory_order_relaxed);
     return static_cast<int>(cudaPeekAtLastError());
@@ -138,6 +153,15 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if ((a->N_pad % 16) != 0 || a->N_pad < a->N || (a->K_pad % 64) != 0) return DDM_E_BAD_ARGUMENT;
     if (!a->out_f32_nchw && ((a->ld_out % 8) != 0 || !aligned16(a->out))) return DDM_E_ALIGNMENT;
     if (a->residual != nullptr && ((a->ld_res % 8) != 0 || !aligned16(a->residual))) return DDM_E_ALIGNMENT;
+    {
+        std::lock_guard<std::mutex> lock(g_plans_mu);
+        auto it = g_plans.find(a);
+        if (it != g_plans.end() && std::memcmp(&it->second.args, a, sizeof(*a)) == 0) {
+            const ConvPlan& c = it->second;
+            ddm::launch_conv(c.tmA0, c.tmA1, c.tmW, c.tmOut, c.tmRes, c.p, g_num_sms, as_stream(stream), g_pdl);
+            return finish(1);
+        }
+    }
 
     ddm::ConvParams p;
     std::memset(&p, 0, sizeof(p));
@@ -394,6 +418,12 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             if (r != 0) return r;
             p.res_tma = 1;
         }
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_plans_mu);
+        if (g_plans.size() >= kMaxPlans) g_plans.clear();
+        ConvPlan& c = g_plans[a];
+        std::memcpy(&c.args, a, sizeof(*a)); c.p = p; c.tmA0 = tmA0; c.tmA1 = tmA1; c.tmW = tmW; c.tmOut = tmOut; c.tmRes = tmRes;
     }
     ddm::launch_conv(tmA0, tmA1, tmW, tmOut, tmRes, p, g_num_sms, as_stream(stream), g_pdl);
     return finish(1);
