@@ -71,27 +71,34 @@ struct alignas(8) LaBars {
     uint64_t pvdone[2];      // pass 1: context MMA finished reading P/V buffer
     uint64_t yfull[2];       // pass 2: Y tile ready
     uint64_t wfull, woutfull, mdone;
+    uint64_t wqfull;         // C = 128: W_q of this image landed (wfull then means W_k | W_v of this image)
     uint32_t tmem_base;
 };
 
 template <int C>
 struct LaSmem {
     static constexpr int kAtoms = C / 64;
-    static constexpr int kNbuf = 4;
+    // C = 64: W_qkv (48 KB) stays resident, W_out is loaded per image into the M^T region, ring of 4 x-tiles.
+    // C = 128: the weights do not fit next to the x ring, so the 64 KB weight region is phased per image -- pass 1: W_k | W_v;
+    //          pass 2: W_q (first half) and M^T (second half) -- W_out goes to the union region between the passes, and the
+    //          ring holds 2 x-tiles of 32 KB.  (The per-image weight reloads come from L2: 0.1 GB per launch at B = 1024.)
+    static constexpr bool kResidentW = C == 64;
+    static constexpr int kNbuf = kResidentW ? 4 : 2;
     static constexpr int kXTile = kAtoms * kTileTok * 128;
-    static constexpr int kWBytes = kAtoms * 384 * 128;
-    static constexpr int off_w = 0;                                   // [atom][384 rows (q|k|v)][128 B]
+    static constexpr int kWBytes = kResidentW ? kAtoms * 384 * 128 : 2 * kAtoms * 128 * 128;
+    static constexpr int off_w = 0;
     static constexpr int off_x = off_w + kWBytes;                     // kNbuf x [atom][128 rows][128 B]
     static constexpr int off_u = off_x + kNbuf * kXTile;              // union region, see below
     static constexpr int kPBytes = 128 * 128;                         // P  [128 ch][64 tok]
     static constexpr int kVBytes = kCtxN * 128;                       // V^T[144 rows][64 tok]
     static constexpr int kUBytes = 2 * kPBytes + 2 * kVBytes;         // 69632
     //   pass 1 : P[0] P[1] V[0] V[1]
-    //   between: ctx (bf16 [2 atoms][128][128 B]) at 0
+    //   between: ctx (bf16 [2 atoms][128][128 B]) at 0  (C = 128: W_out [2 atoms][128 rows][128 B] at 32768)
     //   pass 2 : Qs[0] at 0, Qs[1] at 32768 ([2 atoms][128 tok][128 B] each)
-    static constexpr int off_mt = off_u + kUBytes;                    // M^T [2 atoms][C rows][128 B]; W_out before the M GEMM
-    static constexpr int kMtBytes = 2 * C * 128;
-    static constexpr int off_small = off_mt + kMtBytes;
+    static constexpr int kMtBytes = 2 * C * 128;                      // M^T [2 atoms][C rows][128 B]
+    static constexpr int off_mt = kResidentW ? off_u + kUBytes : off_w + kAtoms * 128 * 128;
+    static constexpr int off_wout = kResidentW ? off_mt : off_u + 32768;      // W_out [2 atoms][C rows][128 B] before the M GEMM
+    static constexpr int off_small = kResidentW ? off_mt + kMtBytes : off_u + kUBytes;
     static constexpr int off_rn = off_small;                          // [kNbuf][128] f32
     static constexpr int off_rnl = off_rn + kNbuf * 128 * 4;          // [kNbuf][128] f32  rn * log2(e)
     static constexpr int off_bias = off_rnl + kNbuf * 128 * 4;        // [C]
@@ -103,6 +110,11 @@ struct LaSmem {
     static constexpr int kTotal = off_bars + static_cast<int>(sizeof(LaBars));
     static_assert(kTotal + 1024 <= 227 * 1024, "shared-memory plan does not fit");
     static_assert(kUBytes >= 65536, "union region must hold two Qs buffers");
+    // shared-memory offset of a 128-row weight block: kind 0 = W_q, 1 = W_k, 2 = W_v; atom = 64-channel slice of the input
+    static constexpr __host__ __device__ int w_block(int kind, int a) {
+        return kResidentW ? off_w + a * (384 * 128) + kind * (128 * 128)
+                          : (kind == 0 ? off_w + a * (128 * 128) : off_w + ((kind - 1) * kAtoms + a) * (128 * 128));
+    }
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -155,6 +167,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_init(&bars->wfull, 1);
         mbar_init(&bars->woutfull, 1);
         mbar_init(&bars->mdone, 1);
+        mbar_init(&bars->wqfull, 1);
         fence_barrier_init();
         prefetch_tmap(&tmX);
         prefetch_tmap(&tmY);
@@ -244,18 +257,22 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             auto load_wout = [&]() {
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&bars->woutfull, static_cast<uint32_t>(L::kMtBytes));
-                    for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_mt + a * (C * 128), &tmWout, &bars->woutfull, a * 64, 0);
+                    for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_wout + a * (C * 128), &tmWout, &bars->woutfull, a * 64, 0);
                 }
                 __syncwarp();
             };
-            if (elect_one()) {     // W_qkv (pre-norm gain folded in) stays resident
-                mbar_arrive_expect_tx(&bars->wfull, static_cast<uint32_t>(L::kWBytes));
-                for (int a = 0; a < kAtoms; ++a)
-                    for (int rb = 0; rb < 3; ++rb)
-                        tma_load_2d(smem + L::off_w + a * (384 * 128) + rb * (128 * 128), &tmWqkv, &bars->wfull, a * 64, rb * 128);
-            }
-            __syncwarp();
-            load_wout();
+            // 128-row blocks of W_qkv (pre-norm gain folded in): kinds [k0, k1) of (q, k, v), all input-channel atoms
+            auto load_w = [&](uint64_t* bar, int k0, int k1) {
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar, static_cast<uint32_t>((k1 - k0) * kAtoms * 128 * 128));
+                    for (int kind = k0; kind < k1; ++kind)
+                        for (int a = 0; a < kAtoms; ++a)
+                            tma_load_2d(smem + L::w_block(kind, a), &tmWqkv, bar, a * 64, kind * 128);
+                }
+                __syncwarp();
+            };
+            if (L::kResidentW) { load_w(&bars->wfull, 0, 3); load_wout(); }      // resident for the CTA's lifetime / first image
+            else load_w(&bars->wfull, 1, 3);                                      // W_k | W_v of the first image
             griddep_wait();        // the weights above are constants; x is the previous kernel's output
             pump();
             int G = 0;
@@ -265,6 +282,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     named_bar_sync(kBarEdone + (j & 1), kPass1Edone);
                     if (j & 1) { released = G + (j >> 1) + 1; pump(); }
                 }
+                if (!L::kResidentW) load_w(&bars->wqfull, 0, 1);     // every [K^T|V^T] MMA has retired: W_q over the W_k half
                 const int G2 = G + T;
                 for (int t = 0; t < T; ++t) {       // pass 2: y tile (written in place over its x tile) -> global
                     named_bar_sync(kBarYdone + (t & 3), kGroupThreads + 32);
@@ -278,7 +296,10 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     released = G2 + t + 1;
                     pump();
                 }
-                if (it + 1 < n_img) load_wout();    // every Y MMA of this image has retired (its epilogue ran)
+                if (it + 1 < n_img) {               // every Q / Y MMA of this image has retired (their epilogues ran)
+                    if (L::kResidentW) load_wout();
+                    else load_w(&bars->wfull, 1, 3);
+                }
             }
             if (elect_one()) bulk_wait_group<0>();
             __syncwarp();
@@ -292,7 +313,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     for (int kind = 0; kind < 2; ++kind) {
 #pragma unroll
                         for (int a = 0; a < kAtoms; ++a) {
-                            const uint64_t ad = desc(sb + L::off_w + a * (384 * 128) + (1 + kind) * (128 * 128));
+                            const uint64_t ad = desc(sb + L::w_block(1 + kind, a));
                             const uint64_t bd = desc(xb + a * (kTileTok * 128));
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
@@ -309,7 +330,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
                     for (int a = 0; a < kAtoms; ++a) {
                         const uint64_t ad = desc(xb + a * (kTileTok * 128));
-                        const uint64_t bd = desc(sb + L::off_w + a * (384 * 128));
+                        const uint64_t bd = desc(sb + L::w_block(0, a));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16(tmem_base + static_cast<uint32_t>((t & 1) * 128), ad + 2u * k, bd + 2u * k, idesc_128, (a | k) ? 1u : 0u);
@@ -318,9 +339,10 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 }
                 __syncwarp();
             };
-            wait_leader(&bars->wfull, 0u);
+            if (L::kResidentW) wait_leader(&bars->wfull, 0u);
             int G = 0;
             for (int it = 0; it < n_img; ++it, G += 2 * T) {
+                if (!L::kResidentW) wait_leader(&bars->wfull, static_cast<uint32_t>(it) & 1u);      // this image's W_k | W_v
                 wait_x(G);
                 tc_fence_after();
                 issue_kv(G, 0);
@@ -340,6 +362,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 named_bar_sync(kBarMtdone, kEpiThreads + 64);      // M^T written: accumulator columns 0..63 are free again
                 tc_fence_after();
                 const int G2 = G + T;
+                if (!L::kResidentW) wait_leader(&bars->wqfull, static_cast<uint32_t>(it) & 1u);     // this image's W_q
                 wait_x(G2);
                 issue_q(G2, 0);
                 if (T > 1) { wait_x(G2 + 1); issue_q(G2 + 1, 1); }
@@ -369,6 +392,13 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 // between the passes: M[(h,d)][c] = ctx[(h,d)][(h',e)] . W_out[c][(h',e)]^T   (W_out sits in the M^T region)
                 named_bar_sync(kBarCdone, kEpiThreads + 32);      // block-diagonal context written (every context MMA retired)
                 TR(30, it);
+                if (!L::kResidentW) {       // the V^T buffers are dead now: W_out into the union region (16-32 KB from L2)
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&bars->woutfull, static_cast<uint32_t>(L::kMtBytes));
+                        for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_wout + a * (C * 128), &tmWout, &bars->woutfull, a * 64, 0);
+                    }
+                    __syncwarp();
+                }
                 wait_leader(&bars->woutfull, ph_w);
                 ph_w ^= 1u;
                 tc_fence_after();
@@ -376,7 +406,7 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
                         const uint64_t ad = desc(sb + L::off_u + a * 16384);
-                        const uint64_t bd = desc(sb + L::off_mt + a * (C * 128));
+                        const uint64_t bd = desc(sb + L::off_wout + a * (C * 128));
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc_y, (a | k) ? 1u : 0u);
                     }
@@ -577,17 +607,19 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             TR(52, it);
             {   // thread = row (h,d) of M; columns c = part * C/4 .. ; stored transposed as M^T[c][(h,d)] (K-major B operand of Y)
                 constexpr int kMc = C / 4;
-                static_assert(kMc == 16, "M epilogue is written for C = 64");
                 const uint32_t mbase = sb + L::off_mt + (row >> 6) * (C * 128) + static_cast<uint32_t>((row & 7) * 2);
                 const int ku = (row & 63) >> 3;
-                uint32_t mr[16];
-                tmem_ld16(t_lane + static_cast<uint32_t>(part * kMc), mr);
-                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = part * kMc + i;
-                    const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(mr[i])));
-                    asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(mbase + c * 128 + static_cast<uint32_t>((ku ^ (c & 7)) << 4)), "h"(hv) : "memory");
+                for (int c16 = 0; c16 < kMc / 16; ++c16) {
+                    uint32_t mr[16];
+                    tmem_ld16(t_lane + static_cast<uint32_t>(part * kMc + c16 * 16), mr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = part * kMc + c16 * 16 + i;
+                        const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(mr[i])));
+                        asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(mbase + c * 128 + static_cast<uint32_t>((ku ^ (c & 7)) << 4)), "h"(hv) : "memory");
+                    }
                 }
             }
             arrive(kBarMtdone, kEpiThreads + 64);
@@ -656,44 +688,57 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 TR(45, t);
                 {
                     constexpr int kCols = C / 2;                      // columns of this thread: half * kCols .. +kCols-1
-                    static_assert(kCols == 32, "Y epilogue is written for C = 64");
-                    uint32_t yr[32];
-                    tmem_ld32(t_lane + 256u + static_cast<uint32_t>(grp * 128 + half * kCols), yr);
-                    // residual x (own row of the tile); the result is written in place.  column c: atom c / 64, unit (c % 64) / 8
-                    const uint32_t xrow = sb + L::off_x + slot * L::kXTile + row * 128;
-                    uint4 xr[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) xr[u] = lds_128u(xrow + static_cast<uint32_t>(((half * 4 + u) ^ sw) << 4));
-                    const float4* bp = reinterpret_cast<const float4*>(bias_s + half * kCols);
-                    const float4* gp = reinterpret_cast<const float4*>(g_s + half * kCols);
-                    float v[32];
-                    tmem_ld_wait();
+                    const uint32_t yacc = t_lane + 256u + static_cast<uint32_t>(grp * 128 + half * kCols);
+                    // sweep 1: sum of squares of (acc + bias) over this thread's columns (the accumulator is read again below:
+                    // TMEM reads are cheap, 64 live fp32 values per thread at C = 128 are not)
                     float s0 = 0.0f, s1 = 0.0f;
+                    uint32_t yr[32];          // C = 64: the thread's 32 columns stay here for sweep 2
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 bb = bp[i];
-                        v[4 * i] = __uint_as_float(yr[4 * i]) + bb.x;
-                        v[4 * i + 1] = __uint_as_float(yr[4 * i + 1]) + bb.y;
-                        v[4 * i + 2] = __uint_as_float(yr[4 * i + 2]) + bb.z;
-                        v[4 * i + 3] = __uint_as_float(yr[4 * i + 3]) + bb.w;
-                        s0 = fmaf(v[4 * i], v[4 * i], s0); s1 = fmaf(v[4 * i + 1], v[4 * i + 1], s1);
-                        s0 = fmaf(v[4 * i + 2], v[4 * i + 2], s0); s1 = fmaf(v[4 * i + 3], v[4 * i + 3], s1);
+                    for (int c32 = 0; c32 < kCols / 32; ++c32) {
+                        tmem_ld32(yacc + static_cast<uint32_t>(c32 * 32), yr);
+                        const float4* bp = reinterpret_cast<const float4*>(bias_s + half * kCols + c32 * 32);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 bb = bp[i];
+                            const float a0 = __uint_as_float(yr[4 * i]) + bb.x, a1 = __uint_as_float(yr[4 * i + 1]) + bb.y;
+                            const float a2 = __uint_as_float(yr[4 * i + 2]) + bb.z, a3 = __uint_as_float(yr[4 * i + 3]) + bb.w;
+                            s0 = fmaf(a0, a0, s0); s1 = fmaf(a1, a1, s1); s0 = fmaf(a2, a2, s0); s1 = fmaf(a3, a3, s1);
+                        }
                     }
                     float* red = red_s + grp * 256;
                     red[half * 128 + row] = s0 + s1;
-                    tc_fence_before();
                     named_bar_sync(bar_g, kGroupThreads);
                     TR(46, t);
                     const float rinv = 1.0f / fmaxf(sqrtf(red[row] + red[128 + row]), 1e-12f);
+                    // sweep 2: normalise, gain, + residual x (own row of the tile); written in place over the x tile.
+                    // column c lives in atom c / 64, 16-byte unit (c % 64) / 8
+                    const uint32_t xrow = sb + L::off_x + slot * L::kXTile + row * 128;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float4 g0 = gp[2 * u], g1 = gp[2 * u + 1];
-                        const float* vv = v + 8 * u;
-                        sts_128u(xrow + static_cast<uint32_t>(((half * 4 + u) ^ sw) << 4),
-                                 pack_bf16x2(fmaf(vv[0] * rinv, g0.x, bf16_lo(xr[u].x)), fmaf(vv[1] * rinv, g0.y, bf16_hi(xr[u].x))),
-                                 pack_bf16x2(fmaf(vv[2] * rinv, g0.z, bf16_lo(xr[u].y)), fmaf(vv[3] * rinv, g0.w, bf16_hi(xr[u].y))),
-                                 pack_bf16x2(fmaf(vv[4] * rinv, g1.x, bf16_lo(xr[u].z)), fmaf(vv[5] * rinv, g1.y, bf16_hi(xr[u].z))),
-                                 pack_bf16x2(fmaf(vv[6] * rinv, g1.z, bf16_lo(xr[u].w)), fmaf(vv[7] * rinv, g1.w, bf16_hi(xr[u].w))));
+                    for (int c32 = 0; c32 < kCols / 32; ++c32) {
+                        const int c0 = half * kCols + c32 * 32;
+                        if (kCols > 32) tmem_ld32(yacc + static_cast<uint32_t>(c32 * 32), yr);
+                        const uint32_t xa = xrow + static_cast<uint32_t>((c0 >> 6) * (kTileTok * 128));
+                        uint4 xr[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) xr[u] = lds_128u(xa + static_cast<uint32_t>(((((c0 & 63) >> 3) + u) ^ sw) << 4));
+                        const float4* bp = reinterpret_cast<const float4*>(bias_s + c0);
+                        const float4* gp = reinterpret_cast<const float4*>(g_s + c0);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 b0 = bp[2 * u], b1 = bp[2 * u + 1], g0 = gp[2 * u], g1 = gp[2 * u + 1];
+                            const uint32_t* yy = yr + 8 * u;
+                            sts_128u(xa + static_cast<uint32_t>(((((c0 & 63) >> 3) + u) ^ sw) << 4),
+                                     pack_bf16x2(fmaf((__uint_as_float(yy[0]) + b0.x) * rinv, g0.x, bf16_lo(xr[u].x)),
+                                                 fmaf((__uint_as_float(yy[1]) + b0.y) * rinv, g0.y, bf16_hi(xr[u].x))),
+                                     pack_bf16x2(fmaf((__uint_as_float(yy[2]) + b0.z) * rinv, g0.z, bf16_lo(xr[u].y)),
+                                                 fmaf((__uint_as_float(yy[3]) + b0.w) * rinv, g0.w, bf16_hi(xr[u].y))),
+                                     pack_bf16x2(fmaf((__uint_as_float(yy[4]) + b1.x) * rinv, g1.x, bf16_lo(xr[u].z)),
+                                                 fmaf((__uint_as_float(yy[5]) + b1.y) * rinv, g1.y, bf16_hi(xr[u].z))),
+                                     pack_bf16x2(fmaf((__uint_as_float(yy[6]) + b1.z) * rinv, g1.z, bf16_lo(xr[u].w)),
+                                                 fmaf((__uint_as_float(yy[7]) + b1.w) * rinv, g1.w, bf16_hi(xr[u].w))));
+                        }
                     }
                 }
                 arrive(kBarYdone + (t & 3), kGroupThreads + 32);
@@ -719,8 +764,9 @@ linattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 }  // namespace
 
 int linattn_fused_prepare_attributes() {
-    return static_cast<int>(cudaFuncSetAttribute(linattn_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 LaSmem<64>::kTotal + 1024));
+    int r = static_cast<int>(cudaFuncSetAttribute(linattn_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, LaSmem<64>::kTotal + 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(linattn_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, LaSmem<128>::kTotal + 1024));
+    return r;
 }
 
 int linattn_trace_read(long long* host, int cap) {
@@ -736,7 +782,7 @@ int linattn_trace_read(long long* host, int cap) {
 }
 
 bool linattn_fused_supported(int C, int n, int heads, int d, int n_mem) {
-    return C == 64 && heads == 4 && d == 32 && n >= kTileTok && (n % kTileTok) == 0 && n_mem >= 0 && n_mem <= 4;
+    return (C == 64 || C == 128) && heads == 4 && d == 32 && n >= kTileTok && (n % kTileTok) == 0 && n_mem >= 0 && n_mem <= 4;
 }
 
 void launch_linattn_fused(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmWqkv, const CUtensorMap& tmWout,
@@ -750,14 +796,15 @@ void launch_linattn_fused(const CUtensorMap& tmX, const CUtensorMap& tmY, const 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = LaSmem<64>::kTotal + 1024;
+    cfg.dynamicSmemBytes = (C == 64 ? LaSmem<64>::kTotal : LaSmem<128>::kTotal) + 1024;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, linattn_fused_kernel<64>, tmX, tmY, tmWqkv, tmWout, p);
+    if (C == 64) cudaLaunchKernelEx(&cfg, linattn_fused_kernel<64>, tmX, tmY, tmWqkv, tmWout, p);
+    else cudaLaunchKernelEx(&cfg, linattn_fused_kernel<128>, tmX, tmY, tmWqkv, tmWout, p);
 }
 
 }  // namespace ddm

@@ -17,15 +17,16 @@ def main():
     lib = _lib.init(0)
     g = torch.Generator().manual_seed(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    shapes = ((1024, 1024), (1024, 256), (256, 4096), (64, 16384), (128, 1024))
+    shapes = ((1024, 1024, 64), (1024, 256, 64), (256, 4096, 64), (64, 16384, 64), (128, 1024, 64),
+              (1024, 256, 128), (1024, 1024, 128), (128, 256, 128))
     if len(sys.argv) > 2:
-        shapes = ((int(sys.argv[1]), int(sys.argv[2])),)
+        shapes = ((int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[4]) if len(sys.argv) > 4 else 64),)
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-    for B, n in shapes:
-        C_, heads, d = 64, 4, 32
+    for B, n, C_ in shapes:
+        heads, d = 4, 32
         hid = heads * d
         x = torch.randn((B, n, C_), generator=g).to("cuda", torch.bfloat16)
-        w_qkv = torch.randn((3 * hid, C_, 1, 1), generator=g) * 0.125
+        w_qkv = torch.randn((3 * hid, C_, 1, 1), generator=g) / C_ ** 0.5
         g_in = torch.ones((1, C_, 1, 1))
         w_out = torch.randn((C_, hid, 1, 1), generator=g) * 0.09
         mem = torch.randn((2, heads, d, 4), generator=g)

@@ -173,7 +173,7 @@ class FakeLib:
         return 0
 
     def ddm_linear_attention_block_supported(self, C_, n, heads, d, n_mem):
-        return 1 if (C_ == 64 and heads == 4 and d == 32 and n >= 128 and n % 128 == 0 and 0 <= n_mem <= 4) else 0
+        return 1 if (C_ in (64, 128) and heads == 4 and d == 32 and n >= 128 and n % 128 == 0 and 0 <= n_mem <= 4) else 0
 
     def ddm_linear_attention_block(self, ref, stream):
         a = ref._obj

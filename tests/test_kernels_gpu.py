@@ -311,17 +311,18 @@ def test_linear_attention(lib, n, heads, d):
     close(out, R.linear_attention_ref(qkv.float(), mem, heads, d), 2e-2)
 
 
+@pytest.mark.parametrize("C_", [64, 128])
 @pytest.mark.parametrize("B,n,wscale,n_mem", [(3, 1024, 1.0, 4), (2, 128, 1.0, 4), (5, 256, 3.0, 4), (300, 256, 1.0, 4), (2, 4096, 1.0, 4),
                                               (1, 16384, 0.5, 2), (3, 384, 1.0, 0)])
-def test_linear_attention_block_fused(lib, B, n, wscale, n_mem):
+def test_linear_attention_block_fused(lib, B, n, wscale, n_mem, C_):
     """ddm_linear_attention_block (one tcgen05 kernel) against the unfused fp32 statement of dd:173-193 + residual."""
     from diffusion_models_b200._lib import LinAttnBlockArgs
     from diffusion_models_b200.packing import linattn_k_shift, norm_gain, pack_conv
-    C_, heads, d = 64, 4, 32
+    heads, d = 4, 32
     hid = heads * d
     assert lib.ddm_linear_attention_block_supported(C_, n, heads, d, n_mem) == 1
     x = dev(rnd((B, n, C_), 200) * (1 + rnd((B, n, 1), 201).abs()), BF)      # rows of different lengths
-    w_qkv = rnd((3 * hid, C_, 1, 1), 202, 0.125 * wscale)
+    w_qkv = rnd((3 * hid, C_, 1, 1), 202, wscale / C_ ** 0.5)
     g_in = rnd((1, C_, 1, 1), 203) * 0.1 + 1
     w_out = rnd((C_, hid, 1, 1), 204, 0.09)
     b_out = dev(rnd((C_,), 205, 0.1))
