@@ -203,6 +203,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     }
     p.total_tiles = p.m_tiles * p.n_tiles;
     p.N = a->N;
+    p.rnorm_out = a->rnorm_out;       // (the shared-memory plan depends on it)
     if (a->norm_g != nullptr && p.n_tiles != 1) return DDM_E_UNSUPPORTED;
     if (a->rnorm_out != nullptr && (p.n_tiles != 1 || a->out_f32_nchw)) return DDM_E_UNSUPPORTED;
     // group taps into slabs (same dx and p, consecutive dy) when the dy shift is expressible as an aligned row offset
@@ -312,6 +313,17 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             f.tmem_cols = f.fold == 3 ? 512 : 256; f.acc_stride = f.tmem_cols / 2;
             int st = 0;
             ddm::conv_smem_plan(f, &st);
+            if (st < 2 && !(g_conv_debug & 67108864)) {
+                // 128 -> 64 (two 64-channel chunks per tap: 144 KB of weights): two 24 KB slab stages and both staging buffers
+                // fit only without the alignment slack.  Resident weights are worth it: streamed, every M tile pulls the whole
+                // matrix through L2 again (288 KB per tile against 48 KB).  DDM_CONV_DEBUG & 67108864 keeps the streamed plan.
+                // Only two stages: the one-slab fold (12 N = 192 MMAs = 1.15 k cycles per stage) is the variant that covers a
+                // slab's L2 latency with the other stage's MMAs (measured at B = 1024: streamed 179 us, resident fold 2
+                // 187 us, resident fold 3 140 us).
+                f.tight_smem = 1;
+                f.fold = 3; f.n_slabs = 1; f.tmem_cols = 512; f.acc_stride = 256;
+                ddm::conv_smem_plan(f, &st);
+            }
             if (st >= 2) { f.num_stages = st; p = f; }
         }
     }

@@ -65,7 +65,7 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
     s.staging_off = s.wres_off + (p.b_resident ? p.k_chunks * s.b_chunk_bytes : 0);
     s.colp_off = s.staging_off + (p.tma_store ? (p.staging_bufs > 1 ? p.staging_bufs : 1) * kTileM * p.block_n * 2 : 0);
     s.red_off = s.colp_off + 3 * p.n_pad * 4;
-    s.bars_off = s.red_off + 2 * kMaxParts * kTileM * 4;
+    s.bars_off = s.red_off + (p.rnorm_out != nullptr ? 2 : 1) * kMaxParts * kTileM * 4;     // red_b only with rnorm_out
     s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
     return s;
 }
@@ -80,9 +80,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ ConvParams p) {
     constexpr int kEpiThreads = 32 * kEpiWarps;
     constexpr int kParts = kEpiWarps / 4;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    if (p.tight_smem && smem != smem_raw) __trap();        // the host did not reserve the alignment slack for this plan
     const SmemPlan plan = make_plan(p, p.num_stages);
     const int stage_bytes = plan.stage_bytes;
     uint8_t* wres = smem + plan.wres_off;
@@ -1027,11 +1028,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 }  // namespace
 
 int conv_smem_plan(const ConvParams& p, int* num_stages) {
-    const int budget = 227 * 1024 - 1024;         // minus the alignment slack
+    const int slack = p.tight_smem ? 0 : 1024;    // alignment slack
+    const int budget = 227 * 1024 - slack;
     int stages = 8;
     while (stages > 0 && make_plan(p, stages).total > budget) --stages;
     *num_stages = stages;
-    return make_plan(p, stages > 0 ? stages : 1).total + 1024;
+    return make_plan(p, stages > 0 ? stages : 1).total + slack;
 }
 
 int conv_trace_read(long long* host, int cap) {

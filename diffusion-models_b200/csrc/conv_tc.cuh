@@ -77,6 +77,8 @@ struct ConvParams {
                                  //   4194304 / 8388608 four epilogue groups everywhere / nowhere
                                  // the product path runs with 0
     int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)
+    int tight_smem;              // 1: the plan only fits without the 1 KB alignment slack: the kernel requires (and checks) that
+                                 // its dynamic shared memory starts 1024-byte aligned (it does when there is no static smem)
     // epilogue
     const float* bias;           // [N] or null
     const float* row_scale;      // [B*H*W] or null : v = acc * row_scale[pixel]

@@ -137,6 +137,9 @@ def test_conv3x3_block_epilogue(lib, B, H, W, Cin, Cout):
     (1, 8, 64, 64, 64, True, True),        # 64 wide: two 32-wide tiles per row, taps cross the tile edge
     (2, 6, 48, 64, 64, True, True),        # 48 wide: second tile half outside the image, ragged rows
     (1, 4, 160, 32, 64, False, True),      # 160 wide, C_in = 32 (half-filled K chunk)
+    (3, 32, 32, 128, 64, False, True),     # 128 -> 64 folded with resident weights (144 KB: the plan without alignment slack)
+    (2, 10, 32, 128, 64, False, True),     # the same, ragged tile rows
+    (160, 32, 32, 128, 64, False, True),   # the same, nine tiles per CTA: the two-stage slab ring wraps many times
 ])
 def test_conv3x3_lean_kernel_variants(lib, B, H, W, Cin, Cout, with_res, with_norm):
     """The lean epilogue kernel's variants (dx-folded / residual by TMA / 32-wide tiles) with the batch-shared
@@ -178,6 +181,21 @@ def test_conv3x3_two_sources_concat(lib):
     out = torch.zeros((B, H, W, 128), dtype=BF, device="cuda")
     ref, _ = run_conv(lib, [a, b], pk, (B, H, W), out, bias=dev(rnd((128,), 23, 0.1)))
     close(out, ref)
+
+
+def test_conv3x3_two_sources_folded_resident(lib):
+    """ups.3.x.block1 of the benchmark net: cat(x, skip) 64 + 64 -> 64 at 32 x 32, Block epilogue, no residual."""
+    from diffusion_models_b200.packing import pack_conv
+    B, H, W = 40, 32, 32
+    a, b = dev(rnd((B, H, W, 64), 220), BF), dev(rnd((B, H, W, 64), 221), BF)
+    pk = pack_conv(rnd((64, 128, 3, 3), 222, (128 * 9) ** -0.5), split=(64, 64))
+    out = torch.zeros((B, H, W, 64), dtype=BF, device="cuda")
+    kw = dict(bias=dev(rnd((64,), 223, 0.1)), norm_g=dev(1 + 0.1 * rnd((64,), 224)) * 8.0, scale_shift=dev(rnd((1, 128), 225, 0.3)), act=1)
+    ref, _ = run_conv(lib, [a, b], pk, (B, H, W), out, **kw)
+    close(out, ref)
+    out2 = torch.zeros_like(out)
+    run_conv(lib, [a, b], pk, (B, H, W), out2, **kw)
+    assert torch.equal(out, out2)
 
 
 def test_conv_wide_output_two_n_tiles(lib):
