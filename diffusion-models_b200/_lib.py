@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libddm_b200.so")
-SOURCES = ["conv_tc.cu", "small_kernels.cu", "attention.cu", "attention_tc.cu", "linattn_tc.cu", "linattn_fused.cu", "stem_tc.cu", "api.cu"]
+SOURCES = ["conv_tc.cu", "small_kernels.cu", "attention.cu", "attention_tc.cu", "linattn_tc.cu", "linattn_fused.cu", "stem_tc.cu", "stem_umma.cu", "api.cu"]
 HEADERS = ["conv_tc.cuh", "kernels.cuh", "ptx.cuh", os.path.join("..", "..", "include", "ddm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]

@@ -129,6 +129,7 @@ static int init_on_current_device(int device) {
     r = ddm::stem_prepare_attributes();
     if (r != 0) return r;
     r = ddm::stem_tc_prepare_attributes();
+    if (r == 0) r = ddm::stem_umma_prepare_attributes();
     if (r != 0) return r;
     r = ddm::linattn_fused_prepare_attributes();
     if (r != 0) return r;
@@ -453,6 +454,10 @@ int ddm_stem_conv(const float* in0, int c0, const float* in1, int c1, const floa
     if (in0 == nullptr || weight == nullptr || bias == nullptr || out_bf16 == nullptr || (ksize % 2) != 1) return DDM_E_BAD_ARGUMENT;
     if ((Cout % 8) != 0 || !aligned16(out_bf16)) return DDM_E_ALIGNMENT;
     if (B > 65535) return DDM_E_UNSUPPORTED;
+    if (!(g_conv_debug & 134217728) && ddm::stem_umma_supported(c0 + c1 + c2, Cout, ksize, H, W)) {   // tcgen05 over an explicit im2col tile
+        ddm::launch_stem_umma(in0, c0, in1, c1, in2, c2, weight, bias, out_bf16, B, H, W, Cout, g_num_sms, as_stream(stream), g_pdl);
+        return finish(1);
+    }
     if (ddm::stem_tc_supported(c0 + c1 + c2, Cout, ksize)) {      // tensor-core path (mma.sync implicit GEMM)
         ddm::launch_stem_tc(in0, c0, in1, c1, in2, c2, weight, bias, out_bf16, B, H, W, Cout, ksize, g_num_sms, as_stream(stream));
         return finish(1);

@@ -33,6 +33,11 @@ void launch_finalize(const float* x, float* y, int unnorm, long long numel, cuda
 void launch_select_row(const float* table, const int* step_counter, float* dst, int row_len, cudaStream_t s);
 void launch_randn(float* x, unsigned long long seed, unsigned long long sid, long long numel, cudaStream_t s);
 
+// stem_umma.cu
+bool stem_umma_supported(int Cin, int Cout, int ks, int H, int W);
+int stem_umma_prepare_attributes();
+void launch_stem_umma(const float* in0, int c0, const float* in1, int c1, const float* in2, int c2, const float* w, const float* b,
+                      void* out, int B, int H, int W, int Cout, int num_sms, cudaStream_t s, bool pdl);
 // stem_tc.cu
 bool stem_tc_supported(int Cin, int Cout, int ks);
 int stem_tc_prepare_attributes();

@@ -278,11 +278,13 @@ def test_conv_persistent_many_tiles(lib):
 
 
 # ------------------------------------------------------------------------------------------------ other kernels
-@pytest.mark.parametrize("cs,B", [((3, 0, 0), 2), ((4, 4, 0), 2), ((3, 3, 2), 2), ((3, 0, 0), 96)])
-def test_stem_conv(lib, cs, B):
-    """B = 96: 1440 tiles > the persistent grid, so every CTA walks several tiles with the next patch prefetched."""
+@pytest.mark.parametrize("cs,B,H,W,Co", [((3, 0, 0), 2, 32, 40, 64), ((4, 4, 0), 2, 32, 40, 64), ((3, 3, 2), 2, 32, 40, 64),
+                                         ((3, 0, 0), 96, 32, 40, 64), ((3, 0, 0), 300, 32, 32, 64), ((2, 2, 0), 3, 10, 24, 32),
+                                         ((1, 0, 0), 2, 7, 9, 128), ((3, 0, 0), 2, 64, 64, 64), ((1, 1, 1), 5, 33, 70, 64)])
+def test_stem_conv(lib, cs, B, H, W, Co):
+    """C_in <= 4: tcgen05 over an explicit im2col tile; more channels: mma.sync.  B = 96 / 300: 1440 / 2400 tiles > the persistent
+    grid, so every CTA walks several tiles with the next patch prefetched; 10 x 24, 7 x 9, 33 x 70: ragged tiles."""
     from diffusion_models_b200.packing import pack_stem
-    H, W, Co = 32, 40, 64
     ins = [dev(rnd((B, c, H, W), 90 + i)) for i, c in enumerate(cs) if c]
     cin = sum(cs)
     wt = rnd((Co, cin, 7, 7), 95, (cin * 49) ** -0.5)
