@@ -19,6 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
 MAX_TAPS = 9
+ABI_VERSION = 2          # DDM_ABI_VERSION of include/ddm_b200.h
 
 
 class ConvArgs(C.Structure):
@@ -38,6 +39,9 @@ class ConvArgs(C.Structure):
         ("out", C.c_void_p), ("out_f32_nchw", C.c_int), ("ld_out", C.c_int),
         ("OH", C.c_int), ("OW", C.c_int), ("oy", C.c_int), ("ox", C.c_int), ("sy", C.c_int), ("sx", C.c_int),
         ("rnorm_out", C.c_void_p),
+        ("rsrc0", C.c_void_p), ("rsrc1", C.c_void_p),
+        ("rC0", C.c_int), ("rC1", C.c_int), ("rld0", C.c_int), ("rld1", C.c_int),
+        ("rbias", C.c_void_p),
     ]
 
 
@@ -59,6 +63,7 @@ EXPORTS = {
     "ddm_error_string": (C.c_char_p, [C.c_int]),
     "ddm_launch_count": (C.c_longlong, []),
     "ddm_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "ddm_conv2d_shortcut_supported": (C.c_int, [C.c_int] * 6),
     "ddm_debug_conv_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "ddm_stem_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -132,7 +137,7 @@ def load() -> C.CDLL:
             for name, (res, args) in EXPORTS.items():
                 fn = getattr(lib, name)
                 fn.restype, fn.argtypes = res, args
-            if lib.ddm_abi_version() != 1:
+            if lib.ddm_abi_version() != ABI_VERSION:
                 raise DdmError("libddm_b200.so ABI version mismatch; rebuild")
             _lib = lib
     return _lib

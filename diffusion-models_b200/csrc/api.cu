@@ -46,7 +46,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 struct ConvPlan {
     ddm_conv_args args;
     ddm::ConvParams p;
-    CUtensorMap tmA0, tmA1, tmW, tmOut, tmRes;
+    CUtensorMap tmA0, tmA1, tmW, tmOut, tmRes, tmR1;
 };
 std::unordered_map<const ddm_conv_args*, ConvPlan> g_plans;
 std::mutex g_plans_mu;
@@ -154,12 +154,20 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if ((a->N_pad % 16) != 0 || a->N_pad < a->N || (a->K_pad % 64) != 0) return DDM_E_BAD_ARGUMENT;
     if (!a->out_f32_nchw && ((a->ld_out % 8) != 0 || !aligned16(a->out))) return DDM_E_ALIGNMENT;
     if (a->residual != nullptr && ((a->ld_res % 8) != 0 || !aligned16(a->residual))) return DDM_E_ALIGNMENT;
+    const bool shortcut = a->rsrc0 != nullptr;
+    if (shortcut) {
+        if (a->residual != nullptr || a->rC0 < 64 || (a->rC0 % 64) != 0 || (a->rld0 % 8) != 0 || a->view != 0) return DDM_E_BAD_ARGUMENT;
+        if (a->rsrc1 != nullptr ? (a->rC1 < 64 || (a->rC1 % 64) != 0 || (a->rld1 % 8) != 0) : a->rC1 != 0) return DDM_E_BAD_ARGUMENT;
+        if (!ddm_conv2d_shortcut_supported(a->N, a->C0 + a->C1, a->rC0, a->rC1, a->H, a->W) || a->ntaps != 9 || a->norm_g == nullptr ||
+            a->rnorm_out != nullptr || a->out_f32_nchw || a->OH != a->H || a->OW != a->W || a->sy != 1 || a->sx != 1 || a->N_pad != 64)
+            return DDM_E_UNSUPPORTED;
+    }
     {
         std::lock_guard<std::mutex> lock(g_plans_mu);
         auto it = g_plans.find(a);
         if (it != g_plans.end() && std::memcmp(&it->second.args, a, sizeof(*a)) == 0) {
             const ConvPlan& c = it->second;
-            ddm::launch_conv(c.tmA0, c.tmA1, c.tmW, c.tmOut, c.tmRes, c.p, g_num_sms, as_stream(stream), g_pdl);
+            ddm::launch_conv(c.tmA0, c.tmA1, c.tmW, c.tmOut, c.tmRes, c.tmR1, c.p, g_num_sms, as_stream(stream), g_pdl);
             return finish(1);
         }
     }
@@ -246,7 +254,10 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     const int ceff0 = a->view == 1 ? 2 * a->C0 : a->C0;
     p.chunks0 = (ceff0 + 63) / 64;
     p.chunks1 = a->src1 != nullptr ? (a->C1 + 63) / 64 : 0;
-    if (a->ntaps * (p.chunks0 + p.chunks1) * 64 != a->K_pad) return DDM_E_BAD_ARGUMENT;
+    p.res_chunks0 = shortcut ? a->rC0 / 64 : 0;
+    p.res_chunks = shortcut ? (a->rC0 + a->rC1) / 64 : 0;
+    p.rbias = a->rbias;
+    if ((a->ntaps * (p.chunks0 + p.chunks1) + p.res_chunks) * 64 != a->K_pad) return DDM_E_BAD_ARGUMENT;
     p.k_chunks = a->ntaps * (p.chunks0 + p.chunks1);
     p.n_pad = a->N_pad;
     if (p.n_pad > ddm::kMaxNPad) return DDM_E_UNSUPPORTED;
@@ -283,13 +294,14 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             if (st >= 2) p.num_stages = st; else { p.staging_bufs = 1; p.fast_epilogue = 0; }
         }
     }
-    p.tmem_cols = pow2_ceil(2 * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
+    if (shortcut && !(p.fast_epilogue && p.b_resident && p.n_tiles == 1 && p.block_n == 64)) return DDM_E_UNSUPPORTED;
+    p.tmem_cols = pow2_ceil((shortcut ? 4 : 2) * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
     p.acc_stride = p.tmem_cols / 2;
     p.acc_stages = 2;
     // dx-folded mode (conv_tc.cuh): plain 3x3, C_out padded to 64, tiles spanning whole image rows inside one warp.
     // It cuts the L2 -> shared-memory traffic of the A slabs (the mainloop bound of these layers) at the price of a
     // heavier epilogue, so it is used where the epilogue has slack: no residual input.  DDM_CONV_DEBUG & 512 disables it.
-    if (p.fast_epilogue && !(g_conv_debug & 512) && a->residual == nullptr && a->ntaps == 9 && a->view == 0 && p.n_tiles == 1 && p.block_n == 64 &&
+    if (p.fast_epilogue && !(g_conv_debug & 512) && a->residual == nullptr && !shortcut && a->ntaps == 9 && a->view == 0 && p.n_tiles == 1 && p.block_n == 64 &&
         a->N_pad == 64 && p.bw == a->W && p.bw >= 8 && p.bw <= 32 && p.bb == 1 && !strided_out) {
         bool canonical = true;
         unsigned seen = 0;
@@ -336,7 +348,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     const bool four_groups_pays = (a->ntaps == 1 && a->norm_g != nullptr && a->residual != nullptr && p.block_n == 64) || qkv_three_tiles;
     if (p.fast_epilogue && ((g_conv_debug & 4194304) || (four_groups_pays && !(g_conv_debug & 8388608))) && !(g_conv_debug & 2048) &&
         p.fold != 3) {
-        const int cols = (p.fold ? p.fold : 1) * p.block_n;
+        const int cols = (p.fold ? p.fold : (shortcut ? 2 : 1)) * p.block_n;
         const int stride = pow2_ceil(cols) < 32 ? 32 : pow2_ceil(cols);
         if (4 * stride <= 512) {
             ddm::ConvParams f = p;
@@ -350,11 +362,11 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // half holds a whole tile (both threads' tiles in flight at once): no ordering needed between the threads.  Otherwise mode 1, alternate stages of
     // the same tile in token order.  DDM_CONV_DEBUG & 32: single issuer; & 16384: always mode 1; & 32768: always mode 2.
     {
-        const int stages_per_tile = p.n_slabs * (p.chunks0 + p.chunks1);
+        const int stages_per_tile = p.n_slabs * (p.chunks0 + p.chunks1) + p.res_chunks;
         p.issue_mode = (g_conv_debug & 32) ? 0 : ((g_conv_debug & 16384) ? 1 : ((g_conv_debug & 32768) ? 2 : ((2 * stages_per_tile <= p.num_stages) ? 2 : 1)));
     }
     if (p.fast_epilogue && !(g_conv_debug & 2048)) {      // four accumulator stages where TMEM has room (DDM_CONV_DEBUG & 2048: two)
-        const int cols = (p.fold ? p.fold : 1) * p.block_n;
+        const int cols = (p.fold ? p.fold : (shortcut ? 2 : 1)) * p.block_n;
         const int stride = pow2_ceil(cols) < 32 ? 32 : pow2_ceil(cols);
         if (4 * stride <= 512) { p.acc_stages = 4; p.acc_stride = stride; p.tmem_cols = 4 * stride; }
     }
@@ -432,14 +444,38 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             p.res_tma = 1;
         }
     }
+    CUtensorMap tmR1 = tmRes;
+    if (shortcut) {       // the shortcut's sources as 128-pixel tile boxes (no halo); tmRes carries the first one
+        auto encode_r = [&](CUtensorMap* tm, const void* base, int C, int ld) -> int {
+            const unsigned long long W = a->W, H = a->H, B = a->B, L = ld;
+            const unsigned long long dims[5] = {static_cast<unsigned long long>(C), W, 1ull, H, B};
+            const unsigned long long str[5] = {1ull, L, L * W, L * W, L * W * H};
+            return encode_bf16_map(tm, base, 5, dims, str, box);
+        };
+        r = encode_r(&tmRes, a->rsrc0, a->rC0, a->rld0);
+        if (r != 0) return r;
+        if (a->rsrc1 != nullptr) {
+            r = encode_r(&tmR1, a->rsrc1, a->rC1, a->rld1);
+            if (r != 0) return r;
+        } else {
+            tmR1 = tmRes;
+        }
+    }
     {
         std::lock_guard<std::mutex> lock(g_plans_mu);
         if (g_plans.size() >= kMaxPlans) g_plans.clear();
         ConvPlan& c = g_plans[a];
-        std::memcpy(&c.args, a, sizeof(*a)); c.p = p; c.tmA0 = tmA0; c.tmA1 = tmA1; c.tmW = tmW; c.tmOut = tmOut; c.tmRes = tmRes;
+        std::memcpy(&c.args, a, sizeof(*a)); c.p = p; c.tmA0 = tmA0; c.tmA1 = tmA1; c.tmW = tmW; c.tmOut = tmOut; c.tmRes = tmRes; c.tmR1 = tmR1;
     }
-    ddm::launch_conv(tmA0, tmA1, tmW, tmOut, tmRes, p, g_num_sms, as_stream(stream), g_pdl);
+    ddm::launch_conv(tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p, g_num_sms, as_stream(stream), g_pdl);
     return finish(1);
+}
+
+int ddm_conv2d_shortcut_supported(int N, int C_in, int rC0, int rC1, int H, int W) {
+    // the lean 64-channel plan with resident weights: 9 x C_in/64 + (rC0 + rC1)/64 chunks of 8 KB next to >= 3 slab stages
+    if (g_conv_debug & 268435456) return 0;
+    if (N != 64 || C_in != 64 || rC0 < 64 || (rC0 % 64) != 0 || (rC1 % 64) != 0 || rC0 + rC1 > 256) return 0;
+    return (W >= 32 && (W % 32) == 0 && H >= 4 && (H % 4) == 0) ? 1 : 0;     // full 32 x 4 tiles
 }
 
 /* debugging aid, not part of the documented ABI surface: drains the conv kernel's device-side event trace */

@@ -62,9 +62,9 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
     s.b_chunk_bytes = p.block_n * (kChunkK * 2);
     s.stage_bytes = s.a_bytes + (p.b_resident ? 0 : p.n_dy * s.b_chunk_bytes);
     s.wres_off = num_stages * s.stage_bytes;
-    s.staging_off = s.wres_off + (p.b_resident ? p.k_chunks * s.b_chunk_bytes : 0);
+    s.staging_off = s.wres_off + (p.b_resident ? (p.k_chunks + p.res_chunks) * s.b_chunk_bytes : 0);
     s.colp_off = s.staging_off + (p.tma_store ? (p.staging_bufs > 1 ? p.staging_bufs : 1) * kTileM * p.block_n * 2 : 0);
-    s.red_off = s.colp_off + 3 * p.n_pad * 4;
+    s.red_off = s.colp_off + (p.res_chunks ? 4 : 3) * p.n_pad * 4;
     s.bars_off = s.red_off + (p.rnorm_out != nullptr ? 2 : 1) * kMaxParts * kTileM * 4;     // red_b only with rnorm_out
     s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
     return s;
@@ -77,7 +77,8 @@ template <int kEpiWarps, bool FAST, int FOLD, int GROUPS>
 __global__ void __launch_bounds__(96 + 32 * kEpiWarps, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
-               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ ConvParams p) {
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmR1,
+               const __grid_constant__ ConvParams p) {
     constexpr int kEpiThreads = 32 * kEpiWarps;
     constexpr int kParts = kEpiWarps / 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -91,6 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     float* col_bias = reinterpret_cast<float*>(smem + plan.colp_off);
     float* col_mul = col_bias + p.n_pad;
     float* col_add = col_mul + p.n_pad;
+    [[maybe_unused]] float* col_rbias = col_add + p.n_pad;              // fused shortcut only
     float* red_a = reinterpret_cast<float*>(smem + plan.red_off);      // [parts][128] partial sum of squares (pre-norm)
     float* red_b = red_a + kMaxParts * kTileM;                            // [parts][128] partial sum of squares (stored row)
     ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(smem + plan.bars_off);
@@ -123,12 +125,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         prefetch_tmap(&tmW);
         prefetch_tmap(&tmOut);
         prefetch_tmap(&tmRes);
+        if (p.res_chunks) prefetch_tmap(&tmR1);
         if (p.b_resident) {       // the weights of this (single) N tile are loaded once per CTA; they do not depend on the
                                   // previous kernel, so the load is in flight before griddep_wait()
             const SmemPlan pl = make_plan(p, p.num_stages);
             const int cpt = p.chunks0 + p.chunks1;
-            mbar_arrive_expect_tx(&bars->w_full, static_cast<uint32_t>(p.k_chunks * pl.b_chunk_bytes));
-            for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_arrive_expect_tx(&bars->w_full, static_cast<uint32_t>((p.k_chunks + p.res_chunks) * pl.b_chunk_bytes));
+            for (int kc = 0; kc < p.k_chunks + p.res_chunks; ++kc) {       // (the shortcut's chunks follow the conv's along K)
                 int slot = kc;
                 if constexpr (FOLD) {       // stacked layout: block (dy, chunk) = [dx=-1 | dx=0 | dx=+1] x 64 rows
                     const int tap = kc / cpt, c = kc - tap * cpt;
@@ -156,6 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         col_bias[n] = (in && p.bias != nullptr) ? __ldg(p.bias + n) : 0.0f;
         col_mul[n] = m;
         col_add[n] = a;
+        if (p.res_chunks) col_rbias[n] = (in && p.rbias != nullptr) ? __ldg(p.rbias + n) : 0.0f;
     }
     tc_fence_before();
     __syncthreads();
@@ -248,6 +252,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         if (++stage == ring_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
+                for (int c = 0; c < p.res_chunks; ++c) {       // fused shortcut: the (unshifted) 128-pixel tiles of its sources
+                    mbar_wait(&bars->empty[base + stage], phase ^ 1u);
+                    if (elect_one()) {
+                        uint8_t* a_dst = smem + (base + stage) * stage_bytes;
+                        mbar_arrive_expect_tx(&bars->full[base + stage], static_cast<uint32_t>(kATileBytes));
+                        if (c < p.res_chunks0) tma_load_5d(a_dst, &tmRes, &bars->full[base + stage], c * kChunkK, x0, 0, y0, b0);
+                        else tma_load_5d(a_dst, &tmR1, &bars->full[base + stage], (c - p.res_chunks0) * kChunkK, x0, 0, y0, b0);
+                    }
+                    __syncwarp();
+                    if (++stage == ring_stages) { stage = 0; phase ^= 1u; }
+                }
                 stage_r[ring] = stage;
                 phase_r[ring] = phase;
             }
@@ -290,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const bool by_tile = p.issue_mode == 2;
             const int ring_stages = by_tile ? (p.num_stages >> 1) : p.num_stages;
             const int ring_base = by_tile ? me * ring_stages : 0;
-            const int stages_per_tile = p.n_slabs * chunks_per_tap;
+            const int stages_per_tile = p.n_slabs * chunks_per_tap + p.res_chunks;
             for (int q = 0; seq_tile(q, n_tile_unused, m_tile_unused); ++q) {
                 if (by_tile && (q & 1) != me) {
                     // issue_mode 2: the issuers take alternate TILES.  Consecutive tiles use different accumulators,
@@ -363,6 +378,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         if (++stage == ring_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
+                for (int c = 0; c < p.res_chunks; ++c) {       // fused shortcut: same hand-over protocol, second accumulator
+                    const bool mine = by_tile ? true : (dual ? ((g & 1) == me) : (me == 0));
+                    if (mine) {
+                        mbar_wait(&bars->full[ring_base + stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_lo = smem_lo + static_cast<uint32_t>(ring_base + stage) * stage_step;
+                        const uint32_t b_lo = wres_lo + static_cast<uint32_t>(p.k_chunks + c) * bchunk_step;
+                        if (elect_one()) {
+                            if (dual) {
+                                uint32_t spins = 0;
+                                while (*issued < g) { if (++spins > (1u << 28)) __trap(); }
+                            }
+                            if (do_mma) {
+                                const uint64_t a_desc = desc_base | static_cast<uint64_t>(a_lo);
+                                const uint64_t b_desc = desc_base | static_cast<uint64_t>(b_lo);
+#pragma unroll
+                                for (int k = 0; k < kChunkK / 16; ++k)
+                                    umma_bf16(d_tmem + p.block_n, a_desc + 2u * k, b_desc + 2u * k, idesc_n64, (c | k) ? 1u : 0u);
+                            }
+                            if (dual) { __threadfence_block(); *issued = g + 1; }
+                            umma_commit(&bars->empty[ring_base + stage]);
+                        }
+                        __syncwarp();
+                        mine_any = true;
+                    }
+                    ++g;
+                    if (++stage == ring_stages) { stage = 0; phase ^= 1u; }
+                }
                 // acc_full expects one arrival per issuer: after this thread's MMAs retire, or at once if it had none
                 if (elect_one()) {
                     if (mine_any) umma_commit(&bars->acc_full[acc]); else if (!by_tile) mbar_arrive(&bars->acc_full[acc]);
@@ -398,6 +441,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const bool act_prescaled = has_act && affine;
         const bool res_smem = p.residual != nullptr;
         const bool res_tma = res_smem && p.res_tma != 0;
+        const bool fused_res = p.res_chunks != 0;      // the shortcut's accumulator (columns block_n ..) is added after the activation
+        const uint32_t sb_rbias = smem_u32(col_rbias);
         uint32_t res_phase = 0;
         const bool want_rs = p.row_scale != nullptr, want_rn = p.rnorm_out != nullptr;
         const bool need_geo = leader_warp || (res_smem && !res_tma) || want_rs || want_rn;   // who needs the tile's coordinates
@@ -586,7 +631,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     upk2(s23, a2, a3);
                     gred_a[part * kTileM + r] = (a0 + a1) + (a2 + a3);
                 }
-                if (one_chunk || have_v1) {   // nothing more to read from TMEM: release the accumulator right away
+                if ((one_chunk || have_v1) && !fused_res) {   // nothing more to read from TMEM: release the accumulator right away
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
@@ -615,7 +660,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int c = c_lo; c < c_hi && !skip; ++c) {
                 uint64_t (&v)[8] = v0;          // the first chunk is already there; later chunks overwrite it (no copies)
                 const int nb = n0 + c * 16;
+                [[maybe_unused]] uint64_t rv[8];
+                if (FOLD == 0 && fused_res) {   // in flight during the activation math below
+                    __syncwarp();
+                    tmem_ld16x2(t_row + p.block_n + c * 16, rv);
+                }
                 if (c == c_lo) {
+                    if (FOLD == 0 && fused_res) tmem_ld_wait();
                 } else if (FOLD != 0 && have_v1) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = v1[j];
@@ -658,6 +709,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int u = (cl & 63) >> 3;                // 16-byte unit inside the 128-byte row
                 const uint32_t s0 = rowp + static_cast<uint32_t>(((u) ^ sw) << 4);
                 const uint32_t s1 = rowp + static_cast<uint32_t>(((u + 1) ^ sw) << 4);
+                if (FOLD == 0 && fused_res) {
+                    const uint32_t ra = sb_rbias + static_cast<uint32_t>(nb) * 4u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const ulonglong2 bb = lds_128(ra + j * 16);
+                        v[2 * j] = fadd2(v[2 * j], fadd2(rv[2 * j], bb.x));
+                        v[2 * j + 1] = fadd2(v[2 * j + 1], fadd2(rv[2 * j + 1], bb.y));
+                    }
+                }
                 if (res_smem) {
                     const uint4 r0 = lds_128u(s0), r1 = lds_128u(s1);
                     v[0] = fadd2(v[0], bf2_to_f2(r0.x)); v[1] = fadd2(v[1], bf2_to_f2(r0.y));
@@ -1059,7 +1119,7 @@ int conv_prepare_attributes() {
 }
 
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                 const CUtensorMap& tmRes, const ConvParams& p, int num_sms, cudaStream_t stream, bool pdl) {
+                 const CUtensorMap& tmRes, const CUtensorMap& tmR1, const ConvParams& p, int num_sms, cudaStream_t stream, bool pdl) {
     int stages = 0;
     const int smem = conv_smem_plan(p, &stages);
     int grid;
@@ -1085,17 +1145,17 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 2 : 1;
     if (p.epi_groups == 4 && p.fold == 2) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 4>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 4>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.epi_groups == 4) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0, 4>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0, 4>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.fold == 3) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.fold == 2) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.fast_epilogue) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0, 2>, tmA0, tmA1, tmW, tmOut, tmRes, p);
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     }
 }
 

@@ -77,6 +77,11 @@ struct ConvParams {
                                  //   4194304 / 8388608 four epilogue groups everywhere / nowhere
                                  // the product path runs with 0
     int tma_store;               // 1: stage the bf16 tile in smem and TMA-store it (needs N % 64 == 0, bf16 output)
+    // fused 1x1 shortcut (ResnetBlock.res_conv): res_chunks extra pipeline stages per tile (the centre-tap tiles of the shortcut's
+    // sources, the first res_chunks0 of them from the first source) multiply the resident weight chunks k_chunks .. into a second
+    // accumulator (TMEM columns block_n .. 2 block_n - 1), which the lean epilogue adds (+ rbias) after the activation
+    int res_chunks, res_chunks0;
+    const float* rbias;
     int tight_smem;              // 1: the plan only fits without the 1 KB alignment slack: the kernel requires (and checks) that
                                  // its dynamic shared memory starts 1024-byte aligned (it does when there is no static smem)
     // epilogue
@@ -96,8 +101,9 @@ struct ConvParams {
     float* rnorm_out;            // [B*OH*OW] or null : 1/max(||out_row||_2, 1e-12) of the stored row
 };
 
+// tmRes: the residual tile's map, or (fused shortcut) the shortcut's first source; tmR1: its second source
 void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                 const CUtensorMap& tmRes, const ConvParams& p, int num_sms, cudaStream_t stream, bool pdl);
+                 const CUtensorMap& tmRes, const CUtensorMap& tmR1, const ConvParams& p, int num_sms, cudaStream_t stream, bool pdl);
 // shared-memory plan: returns total dynamic bytes and the stage count that fits (0 stages = does not fit)
 int conv_smem_plan(const ConvParams& p, int* num_stages);
 int conv_prepare_attributes();

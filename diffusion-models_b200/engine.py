@@ -18,7 +18,7 @@ from . import _lib
 from .arch import AttnSpec, ResBlockSpec, StageSpec, UnetSpec
 import os
 
-from .packing import PackedConv, linattn_k_shift, norm_gain, pack_conv, pack_downsample, pack_linear, pack_stem, pack_upsample
+from .packing import PackedConv, append_shortcut, linattn_k_shift, norm_gain, pack_conv, pack_downsample, pack_linear, pack_stem, pack_upsample
 
 MAX_FUSED_NORM = 256     # one CTA owns a full output row in TMEM only up to 256 columns
 MAX_K_SHIFT = 40.0       # fused linear attention: exp(k - shift) must stay a normal fp32 for k >= -shift
@@ -64,8 +64,9 @@ class PlanOps:
 
     def _conv(self, tag: str, pk: PackedConv, srcs: List[torch.Tensor], out: torch.Tensor, *, domain: Tuple[int, int, int],
               bias=None, row_scale=None, norm_g=None, ss=None, ss_stride=0, act=0, residual=None, out_f32_nchw=False,
-              out_map=(1, 1, 0, 0), rnorm_out=None, ld_src: Optional[List[int]] = None, into=None):
-        wdev = self._dev(pk.weight)
+              out_map=(1, 1, 0, 0), rnorm_out=None, ld_src: Optional[List[int]] = None, into=None, shortcut=None):
+        """`shortcut` = (weight with the 1x1 shortcut appended along K, its sources, its bias): out += W_r . cat(sources) + bias."""
+        wdev = self._dev(pk.weight if shortcut is None else shortcut[0])
         a = _lib.ConvArgs()
         a.src0 = srcs[0].data_ptr()
         a.src1 = srcs[1].data_ptr() if len(srcs) > 1 else None
@@ -80,7 +81,13 @@ class PlanOps:
         for i, (dy, dx, p) in enumerate(pk.taps):
             a.tap_dy[i], a.tap_dx[i], a.tap_p[i] = dy, dx, p
         a.weight = wdev.data_ptr()
-        a.N, a.N_pad, a.K_pad = pk.n, pk.n_pad, pk.k_pad
+        a.N, a.N_pad, a.K_pad = pk.n, pk.n_pad, wdev.shape[1]
+        if shortcut is not None:
+            rs = shortcut[1]
+            a.rsrc0, a.rC0, a.rld0 = rs[0].data_ptr(), rs[0].shape[-1], rs[0].shape[-1]
+            if len(rs) > 1:
+                a.rsrc1, a.rC1, a.rld1 = rs[1].data_ptr(), rs[1].shape[-1], rs[1].shape[-1]
+            a.rbias = _ptr(shortcut[2])
         a.row_scale, a.bias, a.norm_g, a.scale_shift = _ptr(row_scale), _ptr(bias), _ptr(norm_g), _ptr(ss)
         a.ss_stride = ss_stride
         a.act = act
@@ -278,15 +285,16 @@ class UnetEngine(PlanOps):
         self._add("time.ss", lambda s: lib.ddm_small_linear(temb.data_ptr(), td, wss.data_ptr(), bss.data_ptr(),
                                                             ss_out.data_ptr(), width, rows, width, td, 1, 0, s), into)
 
-    def _block_tail(self, tag, pk, srcs, out, h, w, *, bias, g, ss, act, residual, rnorm_out=None):
+    def _block_tail(self, tag, pk, srcs, out, h, w, *, bias, g, ss, act, residual, rnorm_out=None, shortcut=None):
         """conv -> RMSNorm -> scale/shift -> act -> (+residual): fused into the conv epilogue when the output row
         fits one TMEM tile, otherwise conv(+bias) followed by the row-norm kernel."""
         B, lib = self.B, self.lib
         c = pk.n
         if c <= MAX_FUSED_NORM:
             self._conv(tag, pk, srcs, out, domain=(B, h, w), bias=bias, norm_g=g, ss=ss, ss_stride=self.ss_stride,
-                       act=act, residual=residual, rnorm_out=rnorm_out)
+                       act=act, residual=residual, rnorm_out=rnorm_out, shortcut=shortcut)
             return
+        assert shortcut is None
         tmp = self._act(B, h, w, c)
         self._conv(tag + ".gemm", pk, srcs, tmp, domain=(B, h, w), bias=bias)
         rows = B * h * w
@@ -304,20 +312,27 @@ class UnetEngine(PlanOps):
         self._block_tail(rb.name + ".block1", pack_conv(W_[rb.name + ".block1.proj.weight"], split), srcs, h1, h, w,
                          bias=self._f32(rb.name + ".block1.proj.bias"), g=self._dev(norm_gain(W_[rb.name + ".block1.norm.g"])),
                          ss=ss, act=1, residual=None)
-        if rb.c_in != rb.c_out:
-            res = self._act(B, h, w, rb.c_out)
-            self._conv(rb.name + ".res_conv", pack_conv(W_[rb.name + ".res_conv.weight"], split), srcs, res,
-                       domain=(B, h, w), bias=self._f32(rb.name + ".res_conv.bias"))
-        else:
-            res = srcs[0]
-        out = self._act(B, h, w, rb.c_out, rb.name)
+        pk2 = pack_conv(W_[rb.name + ".block2.proj.weight"])
         rn = None
         if want_rnorm and self.fuse_rnorm:
             rn = torch.zeros((B * h * w,), dtype=torch.float32, device=self.device)
             self._keep.append(rn)
-        self._block_tail(rb.name + ".block2", pack_conv(W_[rb.name + ".block2.proj.weight"]), [h1], out, h, w,
+        shortcut = None
+        if rb.c_in == rb.c_out:
+            res = srcs[0]
+        elif (rn is None and not os.environ.get("DDM_NO_FUSED_SHORTCUT") and all(s.shape[-1] % 64 == 0 for s in srcs) and
+              self.lib.ddm_conv2d_shortcut_supported(rb.c_out, rb.c_out, srcs[0].shape[-1], srcs[1].shape[-1] if len(srcs) > 1 else 0, h, w)):
+            # res_conv (1x1, dd:134) rides along block2 as extra K steps into a second accumulator: no launch, no round trip
+            res = None
+            shortcut = (append_shortcut(pk2, W_[rb.name + ".res_conv.weight"], split), srcs, self._f32(rb.name + ".res_conv.bias"))
+        else:
+            res = self._act(B, h, w, rb.c_out)
+            self._conv(rb.name + ".res_conv", pack_conv(W_[rb.name + ".res_conv.weight"], split), srcs, res,
+                       domain=(B, h, w), bias=self._f32(rb.name + ".res_conv.bias"))
+        out = self._act(B, h, w, rb.c_out, rb.name)
+        self._block_tail(rb.name + ".block2", pk2, [h1], out, h, w,
                          bias=self._f32(rb.name + ".block2.proj.bias"), g=self._dev(norm_gain(W_[rb.name + ".block2.norm.g"])),
-                         ss=None, act=1, residual=res, rnorm_out=rn)
+                         ss=None, act=1, residual=res, rnorm_out=rn, shortcut=shortcut)
         self._last_rnorm = (out, rn)
         return out
 

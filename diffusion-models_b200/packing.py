@@ -72,6 +72,14 @@ def pack_conv(weight: torch.Tensor, split: Optional[Sequence[int]] = None,
     return PackedConv(_assemble(per_tap, n), taps, split, n)
 
 
+def append_shortcut(pk: PackedConv, res_weight: torch.Tensor, split: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Weights of a conv with the block's 1x1 shortcut fused (ddm_conv_args.rsrc0, ResnetBlock.res_conv dd:134): the packed
+    shortcut matrix [N_pad, sum of 64-padded source segments] appended to the conv's packed matrix along K."""
+    r = pack_conv(res_weight, split)
+    assert r.n_pad == pk.n_pad and len(r.taps) == 1
+    return torch.cat([pk.weight, r.weight], dim=1).contiguous()
+
+
 def pack_linear(weight: torch.Tensor) -> PackedConv:
     """nn.Linear weight [N, K] as a 1x1 convolution over a token matrix."""
     w = weight.detach().float()

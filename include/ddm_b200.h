@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DDM_ABI_VERSION 1
+#define DDM_ABI_VERSION 2
 
 #define DDM_E_NOT_INITIALISED (-1)
 #define DDM_E_BAD_ARGUMENT (-2)
@@ -83,9 +83,21 @@ typedef struct ddm_conv_args {
     int ld_out;
     int OH, OW, oy, ox, sy, sx; /* tile pixel (b,y,x) is stored at (b, y*sy+oy, x*sx+ox)                        */
     float* rnorm_out;          /* [B*OH*OW] or NULL: 1/max(||stored row||, 1e-12) for a following pre-norm     */
+    /* Fused 1x1 shortcut (ResnetBlock.res_conv + the residual add, dd:134,148), or rsrc0 == NULL:
+     *   out += W_r . cat(rsrc0, rsrc1)[pixel] + rbias, added last, in place of `residual` (which must be NULL).
+     * rsrc*: bf16 [B,H,W,rld*], rC* channels each (multiples of 64; rsrc1 may be NULL).  The shortcut's weights
+     * [N][rC0 + rC1] are appended to `weight` along K: K_pad = taps x segments x 64 + rC0 + rC1.  Runs as extra K
+     * steps into a second accumulator of the same tile; see ddm_conv2d_shortcut_supported. */
+    const void* rsrc0;
+    const void* rsrc1;
+    int rC0, rC1, rld0, rld1;
+    const float* rbias;        /* [N] or NULL                                                                   */
 } ddm_conv_args;
 
 int ddm_conv2d(const ddm_conv_args* args, void* stream);
+/* 1 when ddm_conv2d takes the fused shortcut for a Block-epilogue conv of this shape (3x3 over C_in channels -> N with
+ * RMSNorm, unit stride, H x W images), 0 otherwise (the caller then runs the shortcut as its own 1x1 conv). */
+int ddm_conv2d_shortcut_supported(int N, int C_in, int rC0, int rC1, int H, int W);
 /* Debugging aid: with DDM_CONV_DEBUG & 128 the conv kernel records (tag, clock64) pairs from CTA 0; this drains them to
  * host memory (synchronises the device) and returns the number of pairs.  Not used by the product path. */
 int ddm_debug_conv_trace(long long* host_pairs, int cap);

@@ -80,6 +80,17 @@ class FakeLib:
             srcs.append(self.strided_rows(a.src1, B * hs * ws, a.ld1, a.C1, bf).float().reshape(B, hs, ws, a.C1))
         weight = self.view(a.weight, (a.N_pad, a.K_pad), bf).float()
         taps = [(a.tap_dy[i], a.tap_dx[i], a.tap_p[i]) for i in range(a.ntaps)]
+        shortcut = None
+        if a.rsrc0:        # fused 1x1 shortcut: its weights are the last rC0 + rC1 columns of K
+            rs = [self.strided_rows(a.rsrc0, B * H * W, a.rld0, a.rC0, bf).float()]
+            if a.rsrc1:
+                rs.append(self.strided_rows(a.rsrc1, B * H * W, a.rld1, a.rC1, bf).float())
+            kr = a.rC0 + a.rC1
+            shortcut = torch.cat(rs, dim=1) @ weight[:a.N, a.K_pad - kr:].t()
+            if a.rbias:
+                shortcut = shortcut + self.view(a.rbias, (a.N,), f32)
+            shortcut = shortcut.reshape(B, H, W, a.N)
+            weight = weight[:, :a.K_pad - kr].contiguous()
         N = a.N
         row_scale = self.view(a.row_scale, (B * H * W,), f32)
         bias = self.view(a.bias, (N,), f32)
@@ -97,6 +108,8 @@ class FakeLib:
             res = None
             if a.residual:
                 res = self.strided_rows(a.residual, B * a.OH * a.OW, a.ld_res, a.ld_res, bf).float().reshape(B, a.OH, a.OW, a.ld_res)
+            elif shortcut is not None:
+                res = shortcut
         rn = self.view(a.rnorm_out, (B * a.OH * a.OW,), f32)
         if a.out_f32_nchw:
             R.conv_ref(srcs, weight, N, (B, H, W), taps, view=a.view, row_scale=row_scale, bias=bias, norm_g=g,
@@ -106,6 +119,10 @@ class FakeLib:
                        scale_shift=ss, act=a.act, residual=res, out=outf, out_map=(a.sy, a.sx, a.oy, a.ox), rnorm_out=rn)
             out.copy_(outf.reshape(out.shape).to(bf))
         return 0
+
+    def ddm_conv2d_shortcut_supported(self, N, C_in, rC0, rC1, H, W):
+        return 1 if (N == 64 and C_in == 64 and rC0 >= 64 and rC0 % 64 == 0 and rC1 % 64 == 0 and rC0 + rC1 <= 256 and
+                     W >= 32 and W % 32 == 0 and H >= 4 and H % 4 == 0) else 0
 
     def ddm_stem_conv(self, in0, c0, in1, c1, in2, c2, w, b, out, B, H, W, Cout, ks, stream):
         self.calls += 1

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.ddm_abi_version() == 1
+    assert lib.ddm_abi_version() == 2
     assert b"ddm_init" in lib.ddm_error_string(-1)
     assert lib.ddm_error_string(-3).decode().startswith("unsupported")
 

@@ -63,6 +63,18 @@ def run_conv(lib, srcs, pk, domain, out, **kw):
     a.weight = w.data_ptr()
     a.N, a.N_pad, a.K_pad = pk.n, pk.n_pad, pk.k_pad
     ptr = lambda t: None if t is None else t.data_ptr()
+    sc = kw.get("shortcut")          # (sources, res_conv weight [N, C, 1, 1], split, bias): fused 1x1 shortcut
+    sc_ref = None
+    if sc is not None:
+        from diffusion_models_b200.packing import append_shortcut, pack_conv
+        w = dev(append_shortcut(pk, sc[1], sc[2]))
+        a.weight, a.K_pad = w.data_ptr(), w.shape[1]
+        a.rsrc0, a.rC0, a.rld0 = sc[0][0].data_ptr(), sc[0][0].shape[-1], sc[0][0].shape[-1]
+        if len(sc[0]) > 1:
+            a.rsrc1, a.rC1, a.rld1 = sc[0][1].data_ptr(), sc[0][1].shape[-1], sc[0][1].shape[-1]
+        a.rbias = ptr(sc[3])
+        wr = dev(pack_conv(sc[1], sc[2]).weight).float()[:pk.n]          # bf16-rounded, like the kernel's operand
+        sc_ref = torch.cat([t.float() for t in sc[0]], dim=-1) @ wr.t() + sc[3]
     a.row_scale, a.bias, a.norm_g = ptr(kw.get("row_scale")), ptr(kw.get("bias")), ptr(kw.get("norm_g"))
     ss = kw.get("scale_shift")
     a.scale_shift = ptr(ss)
@@ -82,9 +94,9 @@ def run_conv(lib, srcs, pk, domain, out, **kw):
     check(lib.ddm_conv2d(C.byref(a), stream()))
     ref_out = torch.zeros_like(out, dtype=F32)
     ref_rn = torch.zeros_like(rn) if rn is not None else None
-    R.conv_ref([s.float() for s in srcs], w.float(), pk.n, domain, pk.taps, view=pk.view,
+    R.conv_ref([s.float() for s in srcs], dev(pk.weight).float(), pk.n, domain, pk.taps, view=pk.view,
                row_scale=kw.get("row_scale"), bias=kw.get("bias"), norm_g=kw.get("norm_g"), scale_shift=ss,
-               act=a.act, residual=res.float() if res is not None else None, out=ref_out, out_map=(a.sy, a.sx, a.oy, a.ox),
+               act=a.act, residual=res.float() if res is not None else sc_ref, out=ref_out, out_map=(a.sy, a.sx, a.oy, a.ox),
                out_f32_nchw=nchw, rnorm_out=ref_rn)
     return ref_out, ref_rn
 
@@ -195,6 +207,25 @@ def test_conv3x3_two_sources_folded_resident(lib):
     close(out, ref)
     out2 = torch.zeros_like(out)
     run_conv(lib, [a, b], pk, (B, H, W), out2, **kw)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("B,H,W,rc", [(3, 32, 32, (64, 64)), (150, 32, 32, (64, 64)), (2, 64, 64, (128,)), (1, 8, 32, (64, 64, ))])
+def test_conv3x3_fused_shortcut(lib, B, H, W, rc):
+    """ResnetBlock tail with dim_in != dim_out (dd:134,148): block2's conv + RMSNorm + SiLU with res_conv(cat(x, skip)) + bias riding
+    along as extra K steps into a second accumulator."""
+    from diffusion_models_b200.packing import pack_conv
+    assert lib.ddm_conv2d_shortcut_supported(64, 64, rc[0], rc[1] if len(rc) > 1 else 0, H, W) == 1
+    h1 = dev(rnd((B, H, W, 64), 240), BF)
+    rs = [dev(rnd((B, H, W, c), 241 + i), BF) for i, c in enumerate(rc)]
+    pk = pack_conv(rnd((64, 64, 3, 3), 244, (64 * 9) ** -0.5))
+    wr, br = rnd((64, sum(rc), 1, 1), 245, sum(rc) ** -0.5), dev(rnd((64,), 246, 0.1))
+    kw = dict(bias=dev(rnd((64,), 247, 0.1)), norm_g=dev(1 + 0.1 * rnd((64,), 248)) * 8.0, act=1, shortcut=(rs, wr, rc if len(rc) > 1 else None, br))
+    out = torch.zeros((B, H, W, 64), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [h1], pk, (B, H, W), out, **kw)
+    close(out, ref)
+    out2 = torch.zeros_like(out)
+    run_conv(lib, [h1], pk, (B, H, W), out2, **kw)
     assert torch.equal(out, out2)
 
 
