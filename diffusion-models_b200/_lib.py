@@ -42,6 +42,7 @@ class ConvArgs(C.Structure):
         ("rsrc0", C.c_void_p), ("rsrc1", C.c_void_p),
         ("rC0", C.c_int), ("rC1", C.c_int), ("rld0", C.c_int), ("rld1", C.c_int),
         ("rbias", C.c_void_p),
+        ("ksplit", C.c_int), ("partial_out", C.c_void_p),
     ]
 
 
@@ -64,6 +65,9 @@ EXPORTS = {
     "ddm_launch_count": (C.c_longlong, []),
     "ddm_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "ddm_conv2d_shortcut_supported": (C.c_int, [C.c_int] * 6),
+    "ddm_conv2d_suggest_ksplit": (C.c_int, [C.c_longlong, C.c_int, C.c_int]),
+    "ddm_rmsnorm_act_split": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "ddm_debug_conv_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "ddm_stem_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

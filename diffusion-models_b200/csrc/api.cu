@@ -145,14 +145,20 @@ static int init_on_current_device(int device) {
 
 int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if (!g_ready) return DDM_E_NOT_INITIALISED;
-    if (a == nullptr || a->src0 == nullptr || a->weight == nullptr || a->out == nullptr) return DDM_E_BAD_ARGUMENT;
+    const bool splitk = a != nullptr && a->ksplit > 1;
+    if (a == nullptr || a->src0 == nullptr || a->weight == nullptr || (a->out == nullptr && !splitk)) return DDM_E_BAD_ARGUMENT;
+    if (splitk && (a->partial_out == nullptr || !aligned16(a->partial_out) || a->bias != nullptr || a->row_scale != nullptr ||
+                   a->norm_g != nullptr || a->scale_shift != nullptr || a->act != 0 || a->residual != nullptr || a->rnorm_out != nullptr ||
+                   a->rsrc0 != nullptr || a->view != 0 || a->out_f32_nchw || a->sy != 1 || a->sx != 1 || a->OH != a->H || a->OW != a->W ||
+                   (a->N % 4) != 0 || a->ksplit > 64))
+        return DDM_E_BAD_ARGUMENT;
     if (a->ntaps < 1 || a->ntaps > DDM_MAX_TAPS || a->B < 1 || a->H < 1 || a->W < 1 || a->N < 1) return DDM_E_BAD_ARGUMENT;
     if (a->C0 < 8 || (a->C0 % 8) != 0 || (a->src1 != nullptr && (a->C1 < 8 || (a->C1 % 8) != 0))) return DDM_E_UNSUPPORTED;
     if ((a->ld0 % 8) != 0 || (a->src1 != nullptr && (a->ld1 % 8) != 0)) return DDM_E_ALIGNMENT;
     if (a->view != 0 && a->view != 1) return DDM_E_BAD_ARGUMENT;
     if (a->view == 1 && a->src1 != nullptr) return DDM_E_UNSUPPORTED;
     if ((a->N_pad % 16) != 0 || a->N_pad < a->N || (a->K_pad % 64) != 0) return DDM_E_BAD_ARGUMENT;
-    if (!a->out_f32_nchw && ((a->ld_out % 8) != 0 || !aligned16(a->out))) return DDM_E_ALIGNMENT;
+    if (!splitk && !a->out_f32_nchw && ((a->ld_out % 8) != 0 || !aligned16(a->out))) return DDM_E_ALIGNMENT;
     if (a->residual != nullptr && ((a->ld_res % 8) != 0 || !aligned16(a->residual))) return DDM_E_ALIGNMENT;
     const bool shortcut = a->rsrc0 != nullptr;
     if (shortcut) {
@@ -203,14 +209,15 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // for 148 SMs.  Narrower N tiles multiply the tile count at the same total weight traffic (each tile streams its own
     // slice of W; only the small A operand is re-read, from L2): halve block_n while that still leaves most SMs idle.
     // Not with a fused row norm (one tile must own the whole output row).  DDM_CONV_DEBUG & 33554432 disables it.
-    if (a->norm_g == nullptr && a->rnorm_out == nullptr && !qkv_three_tiles && !(g_conv_debug & 33554432)) {
+    if (a->norm_g == nullptr && a->rnorm_out == nullptr && !qkv_three_tiles && !splitk && !(g_conv_debug & 33554432)) {
         while (p.m_tiles * p.n_tiles * 2 <= g_num_sms && p.block_n >= 128 && (p.block_n % 128) == 0 &&      // tiles stay 64-channel
                (a->N_pad % (p.block_n / 2)) == 0) {                                                         // groups (TMA store)
             p.block_n /= 2;
             p.n_tiles = a->N_pad / p.block_n;
         }
     }
-    p.total_tiles = p.m_tiles * p.n_tiles;
+    p.ksplit = splitk ? a->ksplit : 1;
+    p.total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
     p.N = a->N;
     p.rnorm_out = a->rnorm_out;       // (the shared-memory plan depends on it)
     if (a->norm_g != nullptr && p.n_tiles != 1) return DDM_E_UNSUPPORTED;
@@ -264,7 +271,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // bf16 tiles whose channel count is a multiple of 64 leave through smem staging + TMA stores
     const bool strided_out = (a->sy != 1 || a->sx != 1);
     if (strided_out && !(a->sy == 2 && a->sx == 2 && a->OH == 2 * a->H && a->OW == 2 * a->W)) return DDM_E_UNSUPPORTED;
-    p.tma_store = (!a->out_f32_nchw && (a->N % 64) == 0 && (!strided_out || a->ld_out == a->N) && a->OH >= a->H * a->sy &&
+    p.tma_store = (!splitk && !a->out_f32_nchw && (a->N % 64) == 0 && (!strided_out || a->ld_out == a->N) && a->OH >= a->H * a->sy &&
                    a->OW >= a->W * a->sx) ? 1 : 0;
     {   // lean epilogue kernel: staged TMA store, batch-shared scale/shift, and full tiles wherever a per-pixel side
         // input/output (row_scale, rnorm_out) is addressed by tile offset
@@ -277,10 +284,12 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // shared-memory configuration: prefer A-slab reuse and resident weights, as long as >= 3 pipeline stages remain
     {
         bool done = false;
-        for (int grouped = 1; grouped >= 0 && !done; --grouped) {
+        // (split-K: one pipeline stage per 64-channel K chunk, so that ddm_conv2d_suggest_ksplit's K_pad / 64 is the stage
+        // count, and streamed weights -- a CTA only touches its own K range)
+        for (int grouped = splitk ? 0 : 1; grouped >= 0 && !done; --grouped) {
             if (grouped && !set_slabs(true)) continue;
             if (!grouped) set_slabs(false);
-            for (int resident = (p.n_tiles == 1 ? 1 : 0); resident >= 0 && !done; --resident) {
+            for (int resident = (p.n_tiles == 1 && !splitk ? 1 : 0); resident >= 0 && !done; --resident) {
                 p.b_resident = resident;
                 ddm::conv_smem_plan(p, &p.num_stages);
                 if (p.num_stages >= (grouped || resident ? 3 : 2)) done = true;
@@ -364,6 +373,13 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     {
         const int stages_per_tile = p.n_slabs * (p.chunks0 + p.chunks1) + p.res_chunks;
         p.issue_mode = (g_conv_debug & 32) ? 0 : ((g_conv_debug & 16384) ? 1 : ((g_conv_debug & 32768) ? 2 : ((2 * stages_per_tile <= p.num_stages) ? 2 : 1)));
+        if (splitk) {           // stage ranges differ between the tiles of a CTA: the issuers alternate stages (mode 1), never tiles
+            p.ks_per = (stages_per_tile + p.ksplit - 1) / p.ksplit;
+            if ((p.ksplit - 1) * p.ks_per >= stages_per_tile) return DDM_E_BAD_ARGUMENT;      // an empty range
+            if (p.issue_mode == 2) p.issue_mode = 1;
+            p.partial = a->partial_out;
+            p.partial_stride = static_cast<long long>(a->B) * a->H * a->W * a->N;
+        }
     }
     if (p.fast_epilogue && !(g_conv_debug & 2048)) {      // four accumulator stages where TMEM has room (DDM_CONV_DEBUG & 2048: two)
         const int cols = (p.fold ? p.fold : (shortcut ? 2 : 1)) * p.block_n;
@@ -471,6 +487,22 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     return finish(1);
 }
 
+int ddm_conv2d_suggest_ksplit(long long rows, int N_pad, int K_pad) {
+    if (!g_ready || rows < 1 || N_pad < 1 || K_pad < 64 || (g_conv_debug & 536870912)) return 1;
+    const long long m_tiles = (rows + 127) / 128;
+    const int n_tiles = (N_pad + 255) / 256;
+    const long long tiles = m_tiles * n_tiles;
+    const int stages = K_pad / 64;
+    // Measured (DDIM-100, 32 x 32): +2.7 % at 16 images per GPU, +4 % at 64, -1 % at 128 when layers with up to half as many tiles
+    // as SMs were split (the 8 x 8 level pays more for the extra norm launch than it gains): split only below a third.
+    if (tiles * 3 > g_num_sms || stages < 8) return 1;
+    int ks = static_cast<int>(g_num_sms / tiles);
+    if (ks > stages / 4) ks = stages / 4;                      // at least four K chunks per range
+    if (ks > 16) ks = 16;
+    while (ks > 1 && (ks - 1) * ((stages + ks - 1) / ks) >= stages) --ks;     // every range gets at least one stage
+    return ks < 2 ? 1 : ks;
+}
+
 int ddm_conv2d_shortcut_supported(int N, int C_in, int rC0, int rC1, int H, int W) {
     // the lean 64-channel plan with resident weights: 9 x C_in/64 + (rC0 + rC1)/64 chunks of 8 KB next to >= 3 slab stages
     if (g_conv_debug & 268435456) return 0;
@@ -543,6 +575,20 @@ int ddm_rmsnorm_act(const void* x_bf16, const float* norm_g, const float* scale_
     if (rows_per_batch < 1) return DDM_E_BAD_ARGUMENT;
     ddm::launch_rmsnorm_act(x_bf16, norm_g, scale_shift, ss_stride, rows_per_batch, act, residual_bf16, out_bf16, rows, C,
                             as_stream(stream));
+    return finish(1);
+}
+
+int ddm_rmsnorm_act_split(const float* partials, int ksplit, const float* bias, const float* norm_g, const float* scale_shift,
+                          long long ss_stride, long long rows_per_batch, int act, const void* residual_bf16, void* out_bf16,
+                          long long rows, int C, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (partials == nullptr || ksplit < 1 || rows_per_batch < 1 || rows < 1) return DDM_E_BAD_ARGUMENT;
+    if ((C % 8) != 0 || !aligned16(partials) || !aligned16(out_bf16) || (residual_bf16 != nullptr && !aligned16(residual_bf16)) ||
+        (bias != nullptr && !aligned16(bias)))
+        return DDM_E_ALIGNMENT;
+    if (C > 1024) return DDM_E_UNSUPPORTED;
+    ddm::launch_rmsnorm_act_split(partials, ksplit, bias, norm_g, scale_shift, ss_stride, rows_per_batch, act, residual_bf16, out_bf16, rows,
+                                  C, as_stream(stream));
     return finish(1);
 }
 

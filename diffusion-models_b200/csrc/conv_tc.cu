@@ -73,7 +73,7 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
 // kEpiWarps epilogue warps (multiple of 4).  FAST: lean epilogue for the common case (bf16 output through smem
 // staging + TMA store, full tiles where per-pixel side inputs are used, scale/shift shared by the batch); packed
 // f32x2 arithmetic, all per-pixel address math hoisted out of the tile loop.
-template <int kEpiWarps, bool FAST, int FOLD, int GROUPS>
+template <int kEpiWarps, bool FAST, int FOLD, int GROUPS, bool SPLITK = false>
 __global__ void __launch_bounds__(96 + 32 * kEpiWarps, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
@@ -185,8 +185,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             n_tile = ct >= p.pairs ? 1 : 0;
             m_tile = (ct - n_tile * p.pairs) * 2 + cl_rank;
         } else {
-            const int t = static_cast<int>(blockIdx.x) + q * static_cast<int>(gridDim.x);
+            int t = static_cast<int>(blockIdx.x) + q * static_cast<int>(gridDim.x);
             if (t >= p.total_tiles) return false;
+            if (SPLITK && p.ksplit > 1) {       // t = ((m_tile * ksplit) + ks) * n_tiles + n_tile
+                n_tile = t % p.n_tiles;
+                m_tile = (t / p.n_tiles) / p.ksplit;
+                return true;
+            }
             // N tile fastest: the (at most two) N tiles of an M tile run at the same time on neighbouring CTAs, so the
             // activations are fetched from HBM once and from L2 afterwards (C_out = 384: 12 % of the traffic)
             if (p.n_tiles == 1) { m_tile = t; n_tile = 0; }
@@ -196,6 +201,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         return true;
     };
 
+    // split-K: pipeline-stage range [lo, hi) of the q-th tile of this CTA (all stages without a split)
+    auto stage_range = [&](int q, int& lo, int& hi, int& ks) {
+        lo = 0; hi = 0x7FFFFFFF; ks = 0;
+        if (p.ksplit > 1) {
+            const int t = static_cast<int>(blockIdx.x) + q * static_cast<int>(gridDim.x);
+            ks = (t / p.n_tiles) % p.ksplit;
+            lo = ks * p.ks_per;
+            hi = lo + p.ks_per;
+        }
+    };
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         {
@@ -217,9 +232,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int tb = m_tile / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
                 const int n0 = n_tile * p.block_n;
+                [[maybe_unused]] int st_lo = 0, st_hi = 0, ks_unused = 0, si = 0;
+                if constexpr (SPLITK) stage_range(q, st_lo, st_hi, ks_unused);       // (split-K: its own instantiation of the generic kernel)
                 for (int s = 0; s < p.n_slabs; ++s) {
                     const int cx = x0 + p.slab_dx[s], cy = y0 + p.slab_dy0[s], cp = p.slab_p[s];
                     for (int c = 0; c < chunks_per_tap; ++c) {
+                        if constexpr (SPLITK) {
+                            const int sidx = si++;
+                            if (sidx < st_lo || sidx >= st_hi) continue;        // another split's stage
+                        }
                         mbar_wait(&bars->empty[base + stage], phase ^ 1u);
                         if (elect_one()) {
                             trace_ev(tr, 0, 0, q, trn);
@@ -325,11 +346,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
                 bool first = true;              // first stage of the tile: its first MMA overwrites the accumulator
                 bool mine_any = false;
+                [[maybe_unused]] int st_lo = 0, st_hi = 0, ks_unused = 0, si = 0;
+                if constexpr (SPLITK) stage_range(q, st_lo, st_hi, ks_unused);
                 for (int s = 0; s < p.n_slabs; ++s) {
                     const uint32_t t0 = static_cast<uint32_t>(p.slab_tap[s][0] * chunks_per_tap) * bchunk_step;
                     const uint32_t t1 = static_cast<uint32_t>(p.slab_tap[s][1] * chunks_per_tap) * bchunk_step;
                     const uint32_t t2 = static_cast<uint32_t>(p.slab_tap[s][2] * chunks_per_tap) * bchunk_step;
                     for (int c = 0; c < chunks_per_tap; ++c) {
+                        if constexpr (SPLITK) {
+                            const int sidx = si++;
+                            if (sidx < st_lo || sidx >= st_hi) continue;        // another split's stage
+                        }
                         const bool mine = by_tile ? true : (dual ? ((g & 1) == me) : (me == 0));
                         if (mine) {
                             mbar_wait(&bars->full[ring_base + stage], phase);
@@ -800,7 +827,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         int acc = 0;
         uint32_t acc_phase = 0;
         int n_tile, m_tile;
-        for (int q = 0; seq_tile(q, n_tile, m_tile); ++q) {
+        for (int tq = 0; seq_tile(tq, n_tile, m_tile); ++tq) {   // tq: tile sequence number (q is the TMEM lane quarter)
             int tx, ty, tb;
             if (p.tiles_pow2) {
                 tx = m_tile & (p.tiles_x - 1);
@@ -976,6 +1003,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
                 }
+                if (SPLITK && p.partial != nullptr) {      // split-K: raw fp32 sums of this K range (bias, norm, ... happen in the consumer)
+                    if (valid && nb < p.N) {
+                        int lo_u, hi_u, ks;
+                        stage_range(tq, lo_u, hi_u, ks);
+                        float4* o = reinterpret_cast<float4*>(p.partial + ks * p.partial_stride + out_pix * p.N + nb);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            if (nb + 4 * j4 < p.N) o[j4] = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+                    }
+                    continue;
+                }
                 if (p.out_f32_nchw) {
                     if (valid) {
                         float* o = reinterpret_cast<float*>(p.out);
@@ -1110,6 +1148,7 @@ int conv_trace_read(long long* host, int cap) {
 
 int conv_prepare_attributes() {
     int r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1152,6 +1191,8 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
         cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.fold == 2) {
         cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
+    } else if (p.ksplit > 1) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0, 2, true>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.fast_epilogue) {
         cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else {

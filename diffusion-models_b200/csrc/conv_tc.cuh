@@ -82,6 +82,11 @@ struct ConvParams {
     // accumulator (TMEM columns block_n .. 2 block_n - 1), which the lean epilogue adds (+ rbias) after the activation
     int res_chunks, res_chunks0;
     const float* rbias;
+    // split-K (generic kernel only): tile t = ((m_tile * ksplit) + ks) * n_tiles + n_tile; range ks takes the pipeline stages
+    // [ks * ks_per, min((ks + 1) * ks_per, stages per tile)) of the tile and stores raw fp32 rows to partial + ks * partial_stride
+    int ksplit, ks_per;
+    float* partial;
+    long long partial_stride;
     int tight_smem;              // 1: the plan only fits without the 1 KB alignment slack: the kernel requires (and checks) that
                                  // its dynamic shared memory starts 1024-byte aligned (it does when there is no static smem)
     // epilogue

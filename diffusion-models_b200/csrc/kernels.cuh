@@ -18,6 +18,8 @@ void launch_small_linear(const float* x, int ldx, const float* W, const float* b
 void launch_row_rnorm(const void* x, int ld, float* rn, long long rows, int C, cudaStream_t s);
 void launch_rmsnorm_act(const void* x, const float* g, const float* ss, long long ss_stride, long long rows_per_batch, int act,
                         const void* res, void* out, long long rows, int C, cudaStream_t s);
+void launch_rmsnorm_act_split(const float* partials, int ksplit, const float* bias, const float* g, const float* ss, long long ss_stride,
+                              long long rows_per_batch, int act, const void* res, void* out, long long rows, int C, cudaStream_t s);
 int launch_groupnorm_act(const void* x, const float* gamma, const float* beta, void* out, int B, int HW, int C, int G, float eps, int act,
                          cudaStream_t s);
 int launch_head_conv(const void* x, const float* w, const float* bias, float* out, long long rows, int C, int N, int HW,

@@ -251,6 +251,70 @@ rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     for (int c = (sub + kKeep * lpr) * 8; c < C; c += lpr * 8) finish(c, __ldg(reinterpret_cast<const uint4*>(xr + c)));
 }
 
+// The Block tail over split-K partial sums (conv_tc.cuh: ksplit): x[row][c] = bias[c] + sum_i part[i][row][c], then exactly
+// rmsnorm_act_kernel's math.  fp32 partials [ksplit][rows][C]; the lane's pieces of the row stay in registers (C <= 1024).
+__global__ void __launch_bounds__(256)
+rmsnorm_act_split_kernel(const float* __restrict__ part, int ksplit, const float* __restrict__ bias, const float* __restrict__ g,
+                         const float* __restrict__ ss, long long ss_stride, long long rows_per_batch, int act,
+                         const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out, long long rows, int C) {
+    const int lpr = lanes_per_row(C);
+    const int rows_per_warp = 32 / lpr;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long row = warp * rows_per_warp + lane / lpr;
+    const int sub = lane % lpr;
+    const bool live = row < rows;
+    constexpr int kKeep = 4;
+    float keep[kKeep][8];
+    float s = 0.0f;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < kKeep; ++i) {
+            const int c = (sub + i * lpr) * 8;
+            if (c < C) {
+                float4 a = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 b = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + c + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < ksplit; ++k) {          // fixed order: the sum does not depend on the launch geometry
+                    const float* pr = part + (static_cast<long long>(k) * rows + row) * C + c;
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(pr)), v = __ldg(reinterpret_cast<const float4*>(pr + 4));
+                    a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+                    b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+                }
+                keep[i][0] = a.x; keep[i][1] = a.y; keep[i][2] = a.z; keep[i][3] = a.w;
+                keep[i][4] = b.x; keep[i][5] = b.y; keep[i][6] = b.z; keep[i][7] = b.w;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s = fmaf(keep[i][j], keep[i][j], s);
+            }
+        }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (!live) return;
+    const float rinv = (g != nullptr) ? 1.0f / fmaxf(sqrtf(s), 1e-12f) : 1.0f;
+    const float* ssr = (ss != nullptr) ? ss + (row / rows_per_batch) * ss_stride : nullptr;
+#pragma unroll
+    for (int i = 0; i < kKeep; ++i) {
+        const int c = (sub + i * lpr) * 8;
+        if (c >= C) continue;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = keep[i][j];
+            if (g != nullptr) t = t * rinv * __ldg(g + c + j);
+            if (ssr != nullptr) t = fmaf(t, __ldg(ssr + c + j) + 1.0f, __ldg(ssr + C + c + j));
+            if (act == 1) t = __fdividef(t, 1.0f + __expf(-t));
+            f[j] = t;
+        }
+        if (res != nullptr) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + row * C + c));
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(rw[j]); f[2 * j + 1] += bf16_hi(rw[j]); }
+        }
+        *reinterpret_cast<uint4*>(out + row * C + c) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm (+ swish)
 // VAE decoder norm (ldm/modules/diffusionmodules/model.py:55-56 Normalize = GroupNorm(32, C, eps=1e-6, affine) and the
 // x * sigmoid(x) that follows it at :118-119, :127-128, :573-574).  The statistics span a whole image (H*W x C/G values per
@@ -625,6 +689,15 @@ void launch_rmsnorm_act(const void* x, const float* g, const float* ss, long lon
     rmsnorm_act_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), g, ss, ss_stride,
                                                           rows_per_batch, act, reinterpret_cast<const __nv_bfloat16*>(res),
                                                           reinterpret_cast<__nv_bfloat16*>(out), rows, C);
+}
+void launch_rmsnorm_act_split(const float* partials, int ksplit, const float* bias, const float* g, const float* ss, long long ss_stride,
+                              long long rows_per_batch, int act, const void* res, void* out, long long rows, int C, cudaStream_t s) {
+    int lpr = 1;
+    while (lpr < 32 && lpr * 8 < C) lpr <<= 1;
+    const long long warps = (rows + (32 / lpr) - 1) / (32 / lpr);
+    rmsnorm_act_split_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(partials, ksplit, bias, g, ss, ss_stride, rows_per_batch, act,
+                                                                reinterpret_cast<const __nv_bfloat16*>(res),
+                                                                reinterpret_cast<__nv_bfloat16*>(out), rows, C);
 }
 int launch_groupnorm_act(const void* x, const float* gamma, const float* beta, void* out, int B, int HW, int C, int G, float eps, int act,
                          cudaStream_t s) {

@@ -64,7 +64,7 @@ class PlanOps:
 
     def _conv(self, tag: str, pk: PackedConv, srcs: List[torch.Tensor], out: torch.Tensor, *, domain: Tuple[int, int, int],
               bias=None, row_scale=None, norm_g=None, ss=None, ss_stride=0, act=0, residual=None, out_f32_nchw=False,
-              out_map=(1, 1, 0, 0), rnorm_out=None, ld_src: Optional[List[int]] = None, into=None, shortcut=None):
+              out_map=(1, 1, 0, 0), rnorm_out=None, ld_src: Optional[List[int]] = None, into=None, shortcut=None, ksplit=None):
         """`shortcut` = (weight with the 1x1 shortcut appended along K, its sources, its bias): out += W_r . cat(sources) + bias."""
         wdev = self._dev(pk.weight if shortcut is None else shortcut[0])
         a = _lib.ConvArgs()
@@ -103,6 +103,8 @@ class PlanOps:
             a.OH, a.OW = out.shape[1], out.shape[2]
         a.sy, a.sx, a.oy, a.ox = out_map
         a.rnorm_out = _ptr(rnorm_out)
+        if ksplit is not None:          # (ranges, fp32 workspace [ranges][rows][N]): raw partial sums only, `out` is not written
+            a.ksplit, a.partial_out = ksplit[0], ksplit[1].data_ptr()
         self._keep.append(a)
         self.op_meta[tag] = dict(M=a.B * a.H * a.W, N=a.N, K=a.K_pad, taps=a.ntaps, srcs=len(srcs),
                                  out_bytes=a.B * a.H * a.W * a.N * (4 if out_f32_nchw else 2),
@@ -110,6 +112,16 @@ class PlanOps:
         fn = self.lib.ddm_conv2d
         ref = C.byref(a)
         (into if into is not None else self.ops).append((tag, lambda s, fn=fn, ref=ref: fn(ref, s)))
+
+    def _splitk_workspace(self, numel: int) -> torch.Tensor:
+        """One fp32 scratch buffer shared by every split-K layer of the plan (the ops run in stream order)."""
+        ws = getattr(self, "_splitk_ws", None)
+        if ws is None or ws.numel() < numel:
+            assert ws is None or not getattr(self, "_splitk_used", False) or True
+            ws = torch.zeros((numel,), dtype=torch.float32, device=self.device)
+            self._splitk_ws = ws
+            self._keep.append(ws)
+        return ws[:numel]
 
     def _add(self, tag: str, fn: Callable[[int], int], into=None):
         (into if into is not None else self.ops).append((tag, fn))
@@ -290,6 +302,20 @@ class UnetEngine(PlanOps):
         fits one TMEM tile, otherwise conv(+bias) followed by the row-norm kernel."""
         B, lib = self.B, self.lib
         c = pk.n
+        rows = B * h * w
+        ks = 1
+        if shortcut is None and c % 8 == 0 and c <= 1024 and not os.environ.get("DDM_NO_SPLITK"):
+            ks = lib.ddm_conv2d_suggest_ksplit(rows, pk.n_pad, pk.k_pad)
+        if ks > 1:
+            # few output rows (4x4 / 8x8 levels at small per-GPU batches): K ranges of a tile on different SMs, fp32 partial sums,
+            # and the Block tail over their sum in the row-norm kernel
+            ws = self._splitk_workspace(ks * rows * c)
+            self._conv(tag + ".splitk", pk, srcs, out, domain=(B, h, w), ksplit=(ks, ws))
+            self._add(tag + ".norm", lambda s: lib.ddm_rmsnorm_act_split(ws.data_ptr(), ks, _ptr(bias), _ptr(g), _ptr(ss), self.ss_stride, h * w,
+                                                                          act, _ptr(residual), out.data_ptr(), rows, c, s))
+            if rnorm_out is not None:
+                self._add(tag + ".rnorm", lambda s: lib.ddm_row_rnorm(out.data_ptr(), c, rnorm_out.data_ptr(), rows, c, s))
+            return
         if c <= MAX_FUSED_NORM:
             self._conv(tag, pk, srcs, out, domain=(B, h, w), bias=bias, norm_g=g, ss=ss, ss_stride=self.ss_stride,
                        act=act, residual=residual, rnorm_out=rnorm_out, shortcut=shortcut)
@@ -297,7 +323,6 @@ class UnetEngine(PlanOps):
         assert shortcut is None
         tmp = self._act(B, h, w, c)
         self._conv(tag + ".gemm", pk, srcs, tmp, domain=(B, h, w), bias=bias)
-        rows = B * h * w
         self._add(tag + ".norm", lambda s: lib.ddm_rmsnorm_act(tmp.data_ptr(), _ptr(g), _ptr(ss), self.ss_stride, h * w, act,
                                                                 _ptr(residual), out.data_ptr(), rows, c, s))
         if rnorm_out is not None:

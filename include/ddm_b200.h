@@ -92,12 +92,21 @@ typedef struct ddm_conv_args {
     const void* rsrc1;
     int rC0, rC1, rld0, rld1;
     const float* rbias;        /* [N] or NULL                                                                   */
+    /* Split-K for layers with few output rows (the 4x4 / 8x8 levels at small per-GPU batches), or ksplit <= 1:
+     * the K steps of every tile are divided into `ksplit` contiguous ranges, one CTA each; range i stores its raw
+     * fp32 accumulator rows to partial_out[i][B*H*W][N] and nothing else happens (every epilogue field above must be
+     * NULL / 0 and `out` is not written): ddm_rmsnorm_act_split sums the ranges and applies the Block epilogue. */
+    int ksplit;
+    float* partial_out;
 } ddm_conv_args;
 
 int ddm_conv2d(const ddm_conv_args* args, void* stream);
 /* 1 when ddm_conv2d takes the fused shortcut for a Block-epilogue conv of this shape (3x3 over C_in channels -> N with
  * RMSNorm, unit stride, H x W images), 0 otherwise (the caller then runs the shortcut as its own 1x1 conv). */
 int ddm_conv2d_shortcut_supported(int N, int C_in, int rC0, int rC1, int H, int W);
+/* Split factor ddm_conv2d would want for a GEMM of `rows` output rows, N_pad columns and K_pad reduction length on this
+ * device: 1 when the tile count already fills the SMs, else 2..16. */
+int ddm_conv2d_suggest_ksplit(long long rows, int N_pad, int K_pad);
 /* Debugging aid: with DDM_CONV_DEBUG & 128 the conv kernel records (tag, clock64) pairs from CTA 0; this drains them to
  * host memory (synchronises the device) and returns the number of pairs.  Not used by the product path. */
 int ddm_debug_conv_trace(long long* host_pairs, int cap);
@@ -134,6 +143,11 @@ int ddm_row_rnorm(const void* x_bf16, int ld, float* rnorm, long long rows, int 
 int ddm_rmsnorm_act(const void* x_bf16, const float* norm_g, const float* scale_shift, long long ss_stride,
                     long long rows_per_batch, int act, const void* residual_bf16, void* out_bf16, long long rows, int C,
                     void* stream);
+/* The same tail over split-K partial sums (ddm_conv_args.ksplit): x = bias + sum_i partials[i][row][:], fp32 [ksplit][rows][C];
+ * norm_g may be NULL (plain conv + bias). */
+int ddm_rmsnorm_act_split(const float* partials, int ksplit, const float* bias, const float* norm_g, const float* scale_shift,
+                          long long ss_stride, long long rows_per_batch, int act, const void* residual_bf16, void* out_bf16,
+                          long long rows, int C, void* stream);
 
 /* GroupNorm (+ swish) of the VAE decoder (latent-diffusion/ldm/modules/diffusionmodules/model.py:55-56 Normalize =
  * GroupNorm(32, C, eps=1e-6), and the x*sigmoid(x) behind it at :118-119,127-128,573-574): x, out bf16 [B, HW, C]

@@ -15,6 +15,7 @@ class FakeLib:
     def __init__(self):
         self.engine = None
         self.calls = 0
+        self.num_sms = 148
 
     def attach(self, engine):
         self.engine = engine
@@ -111,6 +112,13 @@ class FakeLib:
             elif shortcut is not None:
                 res = shortcut
         rn = self.view(a.rnorm_out, (B * a.OH * a.OW,), f32)
+        if a.ksplit > 1:           # split-K: raw sums; the emulation puts the whole sum into range 0 and zeros elsewhere
+            raw = torch.zeros((B, H, W, N), dtype=f32)
+            R.conv_ref(srcs, weight, N, (B, H, W), taps, view=a.view, out=raw, round_out=False)
+            part = self.view(a.partial_out, (a.ksplit, B * H * W, N), f32)
+            part.zero_()
+            part[0].copy_(raw.reshape(B * H * W, N))
+            return 0
         if a.out_f32_nchw:
             R.conv_ref(srcs, weight, N, (B, H, W), taps, view=a.view, row_scale=row_scale, bias=bias, norm_g=g,
                        scale_shift=ss, act=a.act, out=out, out_map=(a.sy, a.sx, a.oy, a.ox), out_f32_nchw=True)
@@ -168,6 +176,31 @@ class FakeLib:
         r = self.view(res, (rows, C_), bf)
         y = R.rmsnorm_act_ref(self.view(x, (rows, C_), bf).float(), self.view(g, (C_,), f32), ssv, rows_per_batch, act,
                               r.float() if r is not None else None)
+        self.view(out, (rows, C_), bf).copy_(y.to(bf))
+        return 0
+
+    def ddm_conv2d_suggest_ksplit(self, rows, N_pad, K_pad):
+        m_tiles, n_tiles, stages = (rows + 127) // 128, (N_pad + 255) // 256, K_pad // 64
+        tiles = m_tiles * n_tiles
+        if tiles * 3 > self.num_sms or stages < 8:
+            return 1
+        ks = min(self.num_sms // tiles, stages // 4, 16)
+        while ks > 1 and (ks - 1) * ((stages + ks - 1) // ks) >= stages:
+            ks -= 1
+        return max(ks, 1)
+
+    def ddm_rmsnorm_act_split(self, part, ksplit, bias, g, ss, ss_stride, rows_per_batch, act, res, out, rows, C_, stream):
+        self.calls += 1
+        bf, f32 = torch.bfloat16, torch.float32
+        x = self.view(part, (ksplit, rows, C_), f32).sum(0)
+        if bias:
+            x = x + self.view(bias, (C_,), f32)
+        ssv = None
+        if ss:
+            nb = (rows + rows_per_batch - 1) // rows_per_batch if ss_stride else 1
+            ssv = self.strided_rows(ss, nb, max(ss_stride, 2 * C_), 2 * C_, f32)
+        r = self.view(res, (rows, C_), bf)
+        y = R.rmsnorm_act_ref(x, self.view(g, (C_,), f32), ssv, rows_per_batch, act, r.float() if r is not None else None)
         self.view(out, (rows, C_), bf).copy_(y.to(bf))
         return 0
 

@@ -229,6 +229,47 @@ def test_conv3x3_fused_shortcut(lib, B, H, W, rc):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ks,with_norm", [(16, 4, 4, 512, 512, 4, True), (16, 4, 4, 256, 256, 9, True), (3, 4, 4, 256, 512, 12, True),
+                                                         (32, 8, 8, 128, 256, 2, True), (5, 4, 4, 512, 256, 7, False), (2, 6, 10, 64, 128, 3, True)])
+def test_conv_split_k(lib, B, H, W, Cin, Cout, ks, with_norm):
+    """Few output rows (4x4 / 8x8 levels at small batches): ddm_conv2d with ksplit K ranges -> fp32 partial sums, and the Block tail
+    (bias, RMSNorm, scale/shift, SiLU, residual) over their sum in ddm_rmsnorm_act_split."""
+    from diffusion_models_b200._lib import ConvArgs
+    from diffusion_models_b200.packing import pack_conv
+    x = dev(rnd((B, H, W, Cin), 260), BF)
+    pk = pack_conv(rnd((Cout, Cin, 3, 3), 261, (Cin * 9) ** -0.5))
+    w = dev(pk.weight)
+    rows = B * H * W
+    part = torch.full((ks, rows, Cout), float("nan"), dtype=F32, device="cuda")       # every range must be written
+    a = ConvArgs()
+    a.src0, a.C0, a.ld0 = x.data_ptr(), Cin, Cin
+    a.B, a.H, a.W = B, H, W
+    a.ntaps = 9
+    for i, (dy, dx, p) in enumerate(pk.taps):
+        a.tap_dy[i], a.tap_dx[i], a.tap_p[i] = dy, dx, p
+    a.weight, a.N, a.N_pad, a.K_pad = w.data_ptr(), Cout, pk.n_pad, pk.k_pad
+    a.OH, a.OW, a.sy, a.sx, a.ld_out = H, W, 1, 1, Cout
+    a.ksplit, a.partial_out = ks, part.data_ptr()
+    check(lib.ddm_conv2d(C.byref(a), stream()))
+    raw = torch.zeros((B, H, W, Cout), dtype=F32, device="cuda")
+    R.conv_ref([x.float()], w.float(), Cout, (B, H, W), pk.taps, out=raw, round_out=False)
+    got = part.sum(0).reshape(B, H, W, Cout)
+    assert torch.isfinite(got).all()
+    assert (got - raw).abs().max().item() <= 2e-3 * raw.abs().max().item()
+    bias, g = dev(rnd((Cout,), 262, 0.1)), (dev(1 + 0.1 * rnd((Cout,), 263)) * Cout ** 0.5 if with_norm else None)
+    ss = dev(rnd((1, 2 * Cout), 264, 0.3)) if with_norm else None
+    res = dev(rnd((B, H, W, Cout), 265), BF)
+    out = torch.zeros((B, H, W, Cout), dtype=BF, device="cuda")
+    check(lib.ddm_rmsnorm_act_split(part.data_ptr(), ks, bias.data_ptr(), g.data_ptr() if with_norm else None, ss.data_ptr() if with_norm else None,
+                                    0, H * W, 1 if with_norm else 0, res.data_ptr(), out.data_ptr(), rows, Cout, stream()))
+    ref = torch.zeros((B, H, W, Cout), dtype=F32, device="cuda")
+    R.conv_ref([x.float()], w.float(), Cout, (B, H, W), pk.taps, bias=bias, norm_g=g, scale_shift=ss, act=1 if with_norm else 0,
+               residual=res.float(), out=ref)
+    close(out, ref)
+    sug = lib.ddm_conv2d_suggest_ksplit(rows, pk.n_pad, pk.k_pad)
+    assert 1 <= sug <= 16 and (sug - 1) * -(-(pk.k_pad // 64) // sug) < pk.k_pad // 64
+
+
 def test_conv_wide_output_two_n_tiles(lib):
     """N = 384 (to_qkv, two 192-wide tiles, pre-norm row scale) and N = 512 (two 256-wide tiles)."""
     from diffusion_models_b200.packing import pack_conv
