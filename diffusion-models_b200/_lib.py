@@ -66,6 +66,7 @@ EXPORTS = {
     "ddm_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "ddm_conv2d_shortcut_supported": (C.c_int, [C.c_int] * 6),
     "ddm_conv2d_suggest_ksplit": (C.c_int, [C.c_longlong, C.c_int, C.c_int]),
+    "ddm_conv2d_row_norm_supported": (C.c_int, [C.c_int]),
     "ddm_rmsnorm_act_split": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "ddm_debug_conv_trace": (C.c_int, [C.c_void_p, C.c_int]),

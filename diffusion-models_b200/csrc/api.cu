@@ -220,7 +220,10 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     p.total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
     p.N = a->N;
     p.rnorm_out = a->rnorm_out;       // (the shared-memory plan depends on it)
-    if (a->norm_g != nullptr && p.n_tiles != 1) return DDM_E_UNSUPPORTED;
+    // a normalised row wider than one accumulator: its two N tiles in a CTA pair (conv_tc.cuh: pair_n)
+    const bool pair_norm = a->norm_g != nullptr && p.n_tiles == 2 && ddm_conv2d_row_norm_supported(a->N) && a->N == a->N_pad &&
+                           a->rnorm_out == nullptr && !a->out_f32_nchw && !shortcut && !splitk && g_num_sms >= 2;
+    if (a->norm_g != nullptr && p.n_tiles != 1 && !pair_norm) return DDM_E_UNSUPPORTED;
     if (a->rnorm_out != nullptr && (p.n_tiles != 1 || a->out_f32_nchw)) return DDM_E_UNSUPPORTED;
     // group taps into slabs (same dx and p, consecutive dy) when the dy shift is expressible as an aligned row offset
     auto set_slabs = [&](bool want_group) {
@@ -278,7 +281,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
         const bool full_tiles = (a->W % p.bw == 0) && (a->H % p.bh == 0) && (a->B % p.bb == 0);
         const bool side = (a->row_scale != nullptr) || (a->rnorm_out != nullptr);
         const bool batched_ss = (a->scale_shift != nullptr) && (a->ss_stride != 0);
-        p.fast_epilogue = (p.tma_store && !batched_ss && (!side || (full_tiles && !strided_out)) && !(g_conv_debug & 8)) ? 1 : 0;
+        p.fast_epilogue = (p.tma_store && !batched_ss && (!side || (full_tiles && !strided_out)) && !pair_norm && !(g_conv_debug & 8)) ? 1 : 0;
         p.staging_bufs = 1;
     }
     // shared-memory configuration: prefer A-slab reuse and resident weights, as long as >= 3 pipeline stages remain
@@ -398,6 +401,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // each SM's ~42 B/clk TMA ingest, which multicast does not reduce), so it is off unless DDM_CONV_DEBUG & 64 is set.
     p.cluster = (!p.b_resident && p.m_tiles >= 2 && p.n_tiles <= 2 && (p.block_n % 16) == 0 && (g_conv_debug & 64)) ? 2 : 1;
     p.pairs = (p.m_tiles + 1) / 2;
+    if (pair_norm) { p.cluster = 2; p.pair_n = 1; }
     CUtensorMap tmA0, tmA1, tmW, tmOut;
     const unsigned box[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh), static_cast<unsigned>(p.bb)};
     const unsigned abox[5] = {64u, static_cast<unsigned>(p.bw), 1u, static_cast<unsigned>(p.bh + p.n_dy - 1), static_cast<unsigned>(p.bb)};
@@ -425,7 +429,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     {
         const unsigned long long dims[2] = {static_cast<unsigned long long>(a->K_pad), static_cast<unsigned long long>(a->N_pad)};
         const unsigned long long str[2] = {1ull, static_cast<unsigned long long>(a->K_pad)};
-        const unsigned wbox[2] = {64u, static_cast<unsigned>(p.block_n / p.cluster)};
+        const unsigned wbox[2] = {64u, static_cast<unsigned>(p.block_n / ((p.cluster == 2 && !p.pair_n) ? 2 : 1))};     // multicast: half per CTA
         r = encode_bf16_map(&tmW, a->weight, 2, dims, str, wbox);
         if (r != 0) return r;
     }
@@ -485,6 +489,12 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     }
     ddm::launch_conv(tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p, g_num_sms, as_stream(stream), g_pdl);
     return finish(1);
+}
+
+int ddm_conv2d_row_norm_supported(int N) {
+    if (N <= 256) return 1;                                  // one accumulator holds the row
+    if (g_conv_debug & 1073741824) return 0;
+    return (N <= 512 && (N % 128) == 0) ? 1 : 0;            // two 64-channel-aligned N tiles in a CTA pair
 }
 
 int ddm_conv2d_suggest_ksplit(long long rows, int N_pad, int K_pad) {

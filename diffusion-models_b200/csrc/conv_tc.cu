@@ -13,6 +13,7 @@ struct alignas(8) ConvBarriers {
     uint64_t acc_empty[4];
     uint64_t res_full[4];        // lean epilogue: residual tile landed in group g's staging buffer
     uint64_t w_full;
+    uint64_t xch_full[2];        // pair_n: the peer CTA's row sums of squares of tile parity i have landed in xch[i]
     uint32_t tmem_base;
     int issued;                  // MMA issue token: number of pipeline stages whose MMAs have all been issued
 };
@@ -54,7 +55,7 @@ __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 struct SmemPlan {
-    int a_bytes, b_chunk_bytes, stage_bytes, wres_off, staging_off, colp_off, red_off, bars_off, total;
+    int a_bytes, b_chunk_bytes, stage_bytes, wres_off, staging_off, colp_off, red_off, xch_off, bars_off, total;
 };
 __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stages) {
     SmemPlan s;
@@ -65,7 +66,8 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
     s.staging_off = s.wres_off + (p.b_resident ? (p.k_chunks + p.res_chunks) * s.b_chunk_bytes : 0);
     s.colp_off = s.staging_off + (p.tma_store ? (p.staging_bufs > 1 ? p.staging_bufs : 1) * kTileM * p.block_n * 2 : 0);
     s.red_off = s.colp_off + (p.res_chunks ? 4 : 3) * p.n_pad * 4;
-    s.bars_off = s.red_off + (p.rnorm_out != nullptr ? 2 : 1) * kMaxParts * kTileM * 4;     // red_b only with rnorm_out
+    s.xch_off = s.red_off + (p.rnorm_out != nullptr ? 2 : 1) * kMaxParts * kTileM * 4;     // red_b only with rnorm_out
+    s.bars_off = s.xch_off + (p.pair_n ? 2 * kTileM * 4 : 0);
     s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
     return s;
 }
@@ -106,7 +108,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool affine = (p.norm_g != nullptr) || ss_uniform;
 
     griddep_launch();                                       // the next kernel of the stream may start its own prologue
-    const uint32_t cl_count = p.cluster == 2 ? 2u : 1u;     // a stage is released by the issuers of every CTA of the cluster
+    const bool mcast = p.cluster == 2 && !p.pair_n;         // weights multicast inside CTA pairs (off by default, see api.cu)
+    const uint32_t cl_count = mcast ? 2u : 1u;              // a stage is released by the issuers of every CTA of the cluster
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
             mbar_init(&bars->full[s], 1);
@@ -117,6 +120,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_init(&bars->acc_empty[a], FAST ? kEpiWarps / GROUPS : kEpiWarps);   // FAST: one epilogue group per stage
         }
         mbar_init(&bars->w_full, 1);
+        mbar_init(&bars->xch_full[0], kTileM);
+        mbar_init(&bars->xch_full[1], kTileM);
         for (int g = 0; g < 4; ++g) mbar_init(&bars->res_full[g], 1);
         bars->issued = 0;
         fence_barrier_init();
@@ -179,7 +184,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int cl = p.cluster;
     const int cl_rank = cl == 2 ? static_cast<int>(blockIdx.x & 1) : 0;
     auto seq_tile = [&](int q, int& n_tile, int& m_tile) -> bool {
-        if (cl == 2) {
+        if (cl == 2 && p.pair_n) {      // cluster c: M tiles c, c + n_clusters, ..; the CTA's rank is its N tile
+            const int ct = static_cast<int>(blockIdx.x >> 1) + q * static_cast<int>(gridDim.x >> 1);
+            if (ct >= p.m_tiles) return false;
+            m_tile = ct;
+            n_tile = cl_rank;
+        } else if (cl == 2) {
             const int ct = static_cast<int>(blockIdx.x >> 1) + q * static_cast<int>(gridDim.x >> 1);
             if (ct >= p.pairs * p.n_tiles) return false;
             n_tile = ct >= p.pairs ? 1 : 0;
@@ -258,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 for (int j = 0; j < p.n_dy; ++j) {
                                     uint8_t* b_dst = a_dst + plan.a_bytes + j * plan.b_chunk_bytes;
                                     const int kcol = (p.slab_tap[s][j] * chunks_per_tap + c) * kChunkK;
-                                    if (cl == 2) {      // each CTA fetches half of the rows and multicasts them to both
+                                    if (mcast) {        // each CTA fetches half of the rows and multicasts them to both
                                         const int half_rows = p.block_n >> 1;
                                         tma_load_2d_mc(b_dst + cl_rank * half_rows * (kChunkK * 2), &tmW, &bars->full[base + stage], kcol,
                                                        n0 + cl_rank * half_rows, 0x3);
@@ -394,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             }
                             trace_ev(tr_iss, 1 + me, 3, g, trn);
                             if (dual) { if (!((p.debug & kDbg) & 8192)) __threadfence_block(); *issued = g + 1; }     // pass the token
-                            if (cl == 2) umma_commit_mc(&bars->empty[ring_base + stage], 0x3); else umma_commit(&bars->empty[ring_base + stage]);
+                            if (mcast) umma_commit_mc(&bars->empty[ring_base + stage], 0x3); else umma_commit(&bars->empty[ring_base + stage]);
                             trace_ev(tr, 1 + me, 4, g, trn);
                             }
                             __syncwarp();
@@ -949,8 +959,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (res_smem) cp_async_wait_all();     // own residual copies landed; the barrier publishes everyone's
             named_bar_sync(kBarPre, kEpiThreads);
             float rinv = 1.0f;
-            if (p.norm_g != nullptr)
-                rinv = 1.0f / fmaxf(sqrtf((red_a[r] + red_a[kTileM + r]) + (red_a[2 * kTileM + r] + red_a[3 * kTileM + r])), 1e-12f);
+            if (p.norm_g != nullptr) {
+                float tot = (red_a[r] + red_a[kTileM + r]) + (red_a[2 * kTileM + r] + red_a[3 * kTileM + r]);
+                if (p.pair_n) {      // the other half of the row lives in the peer CTA: swap the halves' sums of squares
+                    float* xch = reinterpret_cast<float*>(smem + plan.xch_off);
+                    const int par = tq & 1;
+                    if (part == 0) {
+                        const uint32_t peer = static_cast<uint32_t>(cl_rank ^ 1);
+                        st_cluster_f32(cluster_map(smem_u32(xch + par * kTileM + r), peer), tot);
+                        mbar_arrive_cluster(cluster_map(smem_u32(&bars->xch_full[par]), peer));
+                    }
+                    if (lane == 0) mbar_wait_cluster(&bars->xch_full[par], static_cast<uint32_t>(tq >> 1) & 1u);
+                    __syncwarp();
+                    const float mine = tot, theirs = xch[par * kTileM + r];
+                    tot = cl_rank == 0 ? mine + theirs : theirs + mine;      // same operand order in both CTAs: identical bits
+                }
+                rinv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+            }
 
             float out_sumsq = 0.0f;
             for (int c = c_lo; c < c_hi; ++c) {
@@ -1163,7 +1188,7 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
     const int smem = conv_smem_plan(p, &stages);
     int grid;
     if (p.cluster == 2) {
-        const int cluster_tiles = p.pairs * p.n_tiles;
+        const int cluster_tiles = p.pair_n ? p.m_tiles : p.pairs * p.n_tiles;
         const int n_clusters = cluster_tiles < num_sms / 2 ? cluster_tiles : num_sms / 2;
         grid = 2 * n_clusters;
     } else {

@@ -87,6 +87,10 @@ struct ConvParams {
     int ksplit, ks_per;
     float* partial;
     long long partial_stride;
+    // pair_n (generic kernel, cluster == 2): the two N tiles of one M tile run in the two CTAs of a cluster, so that a row wider
+    // than one accumulator (C_out = 512) still gets its RMSNorm in the epilogue: the CTAs exchange their per-row sums of squares
+    // through distributed shared memory (remote st + remote mbarrier arrive) once per tile
+    int pair_n;
     int tight_smem;              // 1: the plan only fits without the 1 KB alignment slack: the kernel requires (and checks) that
                                  // its dynamic shared memory starts 1024-byte aligned (it does when there is no static smem)
     // epilogue

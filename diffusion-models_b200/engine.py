@@ -321,6 +321,14 @@ class UnetEngine(PlanOps):
                        act=act, residual=residual, rnorm_out=rnorm_out, shortcut=shortcut)
             return
         assert shortcut is None
+        if (g is not None and not os.environ.get("DDM_NO_PAIR_NORM") and pk.n == pk.n_pad and
+                lib.ddm_conv2d_row_norm_supported(c)):
+            # 512-channel rows: the two 256-column tiles of a row in a CTA pair, RMSNorm in the epilogue (no separate norm launch)
+            self._conv(tag, pk, srcs, out, domain=(B, h, w), bias=bias, norm_g=g, ss=ss, ss_stride=self.ss_stride,
+                       act=act, residual=residual)
+            if rnorm_out is not None:
+                self._add(tag + ".rnorm", lambda s: lib.ddm_row_rnorm(out.data_ptr(), c, rnorm_out.data_ptr(), rows, c, s))
+            return
         tmp = self._act(B, h, w, c)
         self._conv(tag + ".gemm", pk, srcs, tmp, domain=(B, h, w), bias=bias)
         self._add(tag + ".norm", lambda s: lib.ddm_rmsnorm_act(tmp.data_ptr(), _ptr(g), _ptr(ss), self.ss_stride, h * w, act,

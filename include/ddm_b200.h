@@ -107,6 +107,10 @@ int ddm_conv2d_shortcut_supported(int N, int C_in, int rC0, int rC1, int H, int 
 /* Split factor ddm_conv2d would want for a GEMM of `rows` output rows, N_pad columns and K_pad reduction length on this
  * device: 1 when the tile count already fills the SMs, else 2..16. */
 int ddm_conv2d_suggest_ksplit(long long rows, int N_pad, int K_pad);
+/* 1 when ddm_conv2d can apply `norm_g` (RMSNorm over the N outputs of a pixel) in its epilogue for this N: up to 256 columns in
+ * one accumulator, up to 512 (multiples of 128) as two N tiles in a CTA pair exchanging sums of squares over distributed
+ * shared memory (not together with rnorm_out).  Otherwise: ddm_conv2d without norm_g, then ddm_rmsnorm_act. */
+int ddm_conv2d_row_norm_supported(int N);
 /* Debugging aid: with DDM_CONV_DEBUG & 128 the conv kernel records (tag, clock64) pairs from CTA 0; this drains them to
  * host memory (synchronises the device) and returns the number of pairs.  Not used by the product path. */
 int ddm_debug_conv_trace(long long* host_pairs, int cap);

@@ -179,6 +179,9 @@ class FakeLib:
         self.view(out, (rows, C_), bf).copy_(y.to(bf))
         return 0
 
+    def ddm_conv2d_row_norm_supported(self, N):
+        return 1 if (N <= 256 or (N <= 512 and N % 128 == 0)) else 0
+
     def ddm_conv2d_suggest_ksplit(self, rows, N_pad, K_pad):
         m_tiles, n_tiles, stages = (rows + 127) // 128, (N_pad + 255) // 256, K_pad // 64
         tiles = m_tiles * n_tiles

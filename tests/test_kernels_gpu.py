@@ -270,6 +270,26 @@ def test_conv_split_k(lib, B, H, W, Cin, Cout, ks, with_norm):
     assert 1 <= sug <= 16 and (sug - 1) * -(-(pk.k_pad // 64) // sug) < pk.k_pad // 64
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,batched", [(8, 4, 4, 256, 512, False), (37, 4, 4, 512, 512, False), (300, 4, 4, 128, 512, False),
+                                                      (5, 8, 8, 64, 384, True), (2, 6, 10, 128, 512, False)])
+def test_conv_row_norm_in_cta_pair(lib, B, H, W, Cin, Cout, batched):
+    """Block epilogue on rows wider than one accumulator (C_out = 384 / 512): the two N tiles of a row in a CTA pair, sums of
+    squares exchanged through distributed shared memory.  37 / 300 images: 5 / 38 M tiles, i.e. clusters that walk several tiles
+    and an odd tile count; 6 x 10: ragged tiles."""
+    from diffusion_models_b200.packing import pack_conv
+    assert lib.ddm_conv2d_row_norm_supported(Cout) == 1
+    x = dev(rnd((B, H, W, Cin), 280), BF)
+    pk = pack_conv(rnd((Cout, Cin, 3, 3), 281, (Cin * 9) ** -0.5))
+    kw = dict(bias=dev(rnd((Cout,), 282, 0.1)), norm_g=dev(1 + 0.1 * rnd((Cout,), 283)) * Cout ** 0.5,
+              scale_shift=dev(rnd((B if batched else 1, 2 * Cout), 284, 0.3)), act=1, residual=dev(rnd((B, H, W, Cout), 285), BF))
+    out = torch.zeros((B, H, W, Cout), dtype=BF, device="cuda")
+    ref, _ = run_conv(lib, [x], pk, (B, H, W), out, **kw)
+    close(out, ref)
+    out2 = torch.zeros_like(out)
+    run_conv(lib, [x], pk, (B, H, W), out2, **kw)
+    assert torch.equal(out, out2)
+
+
 def test_conv_wide_output_two_n_tiles(lib):
     """N = 384 (to_qkv, two 192-wide tiles, pre-norm row scale) and N = 512 (two 256-wide tiles)."""
     from diffusion_models_b200.packing import pack_conv
