@@ -165,7 +165,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
         if (a->residual != nullptr || a->rC0 < 64 || (a->rC0 % 64) != 0 || (a->rld0 % 8) != 0 || a->view != 0) return DDM_E_BAD_ARGUMENT;
         if (a->rsrc1 != nullptr ? (a->rC1 < 64 || (a->rC1 % 64) != 0 || (a->rld1 % 8) != 0) : a->rC1 != 0) return DDM_E_BAD_ARGUMENT;
         if (!ddm_conv2d_shortcut_supported(a->N, a->C0 + a->C1, a->rC0, a->rC1, a->H, a->W) || a->ntaps != 9 || a->norm_g == nullptr ||
-            a->rnorm_out != nullptr || a->out_f32_nchw || a->OH != a->H || a->OW != a->W || a->sy != 1 || a->sx != 1 || a->N_pad != 64)
+            a->rnorm_out != nullptr || a->out_f32_nchw || a->OH != a->H || a->OW != a->W || a->sy != 1 || a->sx != 1 || a->N_pad != a->N)
             return DDM_E_UNSUPPORTED;
     }
     {
@@ -306,7 +306,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             if (st >= 2) p.num_stages = st; else { p.staging_bufs = 1; p.fast_epilogue = 0; }
         }
     }
-    if (shortcut && !(p.fast_epilogue && p.b_resident && p.n_tiles == 1 && p.block_n == 64)) return DDM_E_UNSUPPORTED;
+    if (shortcut && !(p.fast_epilogue && p.n_tiles == 1 && (p.block_n == 64 || p.block_n == 128))) return DDM_E_UNSUPPORTED;
     p.tmem_cols = pow2_ceil((shortcut ? 4 : 2) * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
     p.acc_stride = p.tmem_cols / 2;
     p.acc_stages = 2;
@@ -514,10 +514,14 @@ int ddm_conv2d_suggest_ksplit(long long rows, int N_pad, int K_pad) {
 }
 
 int ddm_conv2d_shortcut_supported(int N, int C_in, int rC0, int rC1, int H, int W) {
-    // the lean 64-channel plan with resident weights: 9 x C_in/64 + (rC0 + rC1)/64 chunks of 8 KB next to >= 3 slab stages
+    // the lean plan with a second accumulator: 64 channels (resident weights: 9 x C_in/64 + (rC0 + rC1)/64 chunks of 8 KB next to
+    // >= 3 slab stages) or 128 channels (streamed weights, 2 x (128 + 128) TMEM columns)
     if (g_conv_debug & 268435456) return 0;
-    if (N != 64 || C_in != 64 || rC0 < 64 || (rC0 % 64) != 0 || (rC1 % 64) != 0 || rC0 + rC1 > 256) return 0;
-    return (W >= 32 && (W % 32) == 0 && H >= 4 && (H % 4) == 0) ? 1 : 0;     // full 32 x 4 tiles
+    if ((N != 64 && N != 128) || C_in != N || rC0 < 64 || (rC0 % 64) != 0 || (rC1 % 64) != 0 || rC0 + rC1 > 256) return 0;
+    const int bw = W >= 32 ? 32 : pow2_ceil(W);             // full tiles of one image (ddm_conv2d's tile box)
+    if (bw * H < 128) return 0;
+    const int bh = 128 / bw;
+    return ((W % bw) == 0 && (H % bh) == 0) ? 1 : 0;
 }
 
 /* debugging aid, not part of the documented ABI surface: drains the conv kernel's device-side event trace */

@@ -287,9 +287,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     mbar_wait(&bars->empty[base + stage], phase ^ 1u);
                     if (elect_one()) {
                         uint8_t* a_dst = smem + (base + stage) * stage_bytes;
-                        mbar_arrive_expect_tx(&bars->full[base + stage], static_cast<uint32_t>(kATileBytes));
+                        mbar_arrive_expect_tx(&bars->full[base + stage], static_cast<uint32_t>(kATileBytes + (p.b_resident ? 0 : plan.b_chunk_bytes)));
                         if (c < p.res_chunks0) tma_load_5d(a_dst, &tmRes, &bars->full[base + stage], c * kChunkK, x0, 0, y0, b0);
                         else tma_load_5d(a_dst, &tmR1, &bars->full[base + stage], (c - p.res_chunks0) * kChunkK, x0, 0, y0, b0);
+                        if (!p.b_resident)       // streamed weights: the shortcut's chunk rides in the stage's first weight slot
+                            tma_load_2d(a_dst + plan.a_bytes, &tmW, &bars->full[base + stage], (p.k_chunks + c) * kChunkK, n0);
                     }
                     __syncwarp();
                     if (++stage == ring_stages) { stage = 0; phase ^= 1u; }
@@ -421,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         mbar_wait(&bars->full[ring_base + stage], phase);
                         tc_fence_after();
                         const uint32_t a_lo = smem_lo + static_cast<uint32_t>(ring_base + stage) * stage_step;
-                        const uint32_t b_lo = wres_lo + static_cast<uint32_t>(p.k_chunks + c) * bchunk_step;
+                        const uint32_t b_lo = resident ? wres_lo + static_cast<uint32_t>(p.k_chunks + c) * bchunk_step : a_lo + b_in_stage;
                         if (elect_one()) {
                             if (dual) {
                                 uint32_t spins = 0;

@@ -129,8 +129,12 @@ class FakeLib:
         return 0
 
     def ddm_conv2d_shortcut_supported(self, N, C_in, rC0, rC1, H, W):
-        return 1 if (N == 64 and C_in == 64 and rC0 >= 64 and rC0 % 64 == 0 and rC1 % 64 == 0 and rC0 + rC1 <= 256 and
-                     W >= 32 and W % 32 == 0 and H >= 4 and H % 4 == 0) else 0
+        if N not in (64, 128) or C_in != N or rC0 < 64 or rC0 % 64 or rC1 % 64 or rC0 + rC1 > 256:
+            return 0
+        bw = 32 if W >= 32 else 1 << max(W - 1, 0).bit_length()
+        if bw * H < 128:
+            return 0
+        return 1 if (W % bw == 0 and H % (128 // bw) == 0) else 0
 
     def ddm_stem_conv(self, in0, c0, in1, c1, in2, c2, w, b, out, B, H, W, Cout, ks, stream):
         self.calls += 1

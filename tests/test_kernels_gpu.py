@@ -210,18 +210,19 @@ def test_conv3x3_two_sources_folded_resident(lib):
     assert torch.equal(out, out2)
 
 
-@pytest.mark.parametrize("B,H,W,rc", [(3, 32, 32, (64, 64)), (150, 32, 32, (64, 64)), (2, 64, 64, (128,)), (1, 8, 32, (64, 64, ))])
-def test_conv3x3_fused_shortcut(lib, B, H, W, rc):
+@pytest.mark.parametrize("B,H,W,rc,N", [(3, 32, 32, (64, 64), 64), (150, 32, 32, (64, 64), 64), (2, 64, 64, (128,), 64), (1, 8, 32, (64, 64), 64),
+                                        (5, 16, 16, (128, 64), 128), (300, 16, 16, (128, 64), 128), (2, 32, 32, (128,), 128)])
+def test_conv3x3_fused_shortcut(lib, B, H, W, rc, N):
     """ResnetBlock tail with dim_in != dim_out (dd:134,148): block2's conv + RMSNorm + SiLU with res_conv(cat(x, skip)) + bias riding
     along as extra K steps into a second accumulator."""
     from diffusion_models_b200.packing import pack_conv
-    assert lib.ddm_conv2d_shortcut_supported(64, 64, rc[0], rc[1] if len(rc) > 1 else 0, H, W) == 1
-    h1 = dev(rnd((B, H, W, 64), 240), BF)
+    assert lib.ddm_conv2d_shortcut_supported(N, N, rc[0], rc[1] if len(rc) > 1 else 0, H, W) == 1
+    h1 = dev(rnd((B, H, W, N), 240), BF)
     rs = [dev(rnd((B, H, W, c), 241 + i), BF) for i, c in enumerate(rc)]
-    pk = pack_conv(rnd((64, 64, 3, 3), 244, (64 * 9) ** -0.5))
-    wr, br = rnd((64, sum(rc), 1, 1), 245, sum(rc) ** -0.5), dev(rnd((64,), 246, 0.1))
-    kw = dict(bias=dev(rnd((64,), 247, 0.1)), norm_g=dev(1 + 0.1 * rnd((64,), 248)) * 8.0, act=1, shortcut=(rs, wr, rc if len(rc) > 1 else None, br))
-    out = torch.zeros((B, H, W, 64), dtype=BF, device="cuda")
+    pk = pack_conv(rnd((N, N, 3, 3), 244, (N * 9) ** -0.5))
+    wr, br = rnd((N, sum(rc), 1, 1), 245, sum(rc) ** -0.5), dev(rnd((N,), 246, 0.1))
+    kw = dict(bias=dev(rnd((N,), 247, 0.1)), norm_g=dev(1 + 0.1 * rnd((N,), 248)) * N ** 0.5, act=1, shortcut=(rs, wr, rc if len(rc) > 1 else None, br))
+    out = torch.zeros((B, H, W, N), dtype=BF, device="cuda")
     ref, _ = run_conv(lib, [h1], pk, (B, H, W), out, **kw)
     close(out, ref)
     out2 = torch.zeros_like(out)
