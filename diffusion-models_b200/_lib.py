@@ -43,6 +43,7 @@ class ConvArgs(C.Structure):
         ("rC0", C.c_int), ("rC1", C.c_int), ("rld0", C.c_int), ("rld1", C.c_int),
         ("rbias", C.c_void_p),
         ("ksplit", C.c_int), ("partial_out", C.c_void_p),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_n", C.c_int),
     ]
 
 
@@ -67,6 +68,7 @@ EXPORTS = {
     "ddm_conv2d_shortcut_supported": (C.c_int, [C.c_int] * 6),
     "ddm_conv2d_suggest_ksplit": (C.c_int, [C.c_longlong, C.c_int, C.c_int]),
     "ddm_conv2d_row_norm_supported": (C.c_int, [C.c_int]),
+    "ddm_conv2d_head_supported": (C.c_int, [C.c_int] * 4),
     "ddm_rmsnorm_act_split": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "ddm_debug_conv_trace": (C.c_int, [C.c_void_p, C.c_int]),

@@ -146,7 +146,16 @@ static int init_on_current_device(int device) {
 int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if (!g_ready) return DDM_E_NOT_INITIALISED;
     const bool splitk = a != nullptr && a->ksplit > 1;
-    if (a == nullptr || a->src0 == nullptr || a->weight == nullptr || (a->out == nullptr && !splitk)) return DDM_E_BAD_ARGUMENT;
+    const bool head = a != nullptr && a->head_out != nullptr;
+    if (a == nullptr || a->src0 == nullptr || a->weight == nullptr || (a->out == nullptr && !splitk && !head)) return DDM_E_BAD_ARGUMENT;
+    if (head) {
+        if (a->head_w == nullptr || a->head_b == nullptr || splitk || a->out_f32_nchw || a->rnorm_out != nullptr || a->view != 0 ||
+            a->sy != 1 || a->sx != 1 || a->OH != a->H || a->OW != a->W)
+            return DDM_E_BAD_ARGUMENT;
+        if (!ddm_conv2d_head_supported(a->N, a->head_n, a->H, a->W) || a->N_pad != a->N || a->norm_g == nullptr ||
+            (a->residual == nullptr && a->rsrc0 == nullptr))       // (plain convs take the dx-folded kernels, which have no head)
+            return DDM_E_UNSUPPORTED;
+    }
     if (splitk && (a->partial_out == nullptr || !aligned16(a->partial_out) || a->bias != nullptr || a->row_scale != nullptr ||
                    a->norm_g != nullptr || a->scale_shift != nullptr || a->act != 0 || a->residual != nullptr || a->rnorm_out != nullptr ||
                    a->rsrc0 != nullptr || a->view != 0 || a->out_f32_nchw || a->sy != 1 || a->sx != 1 || a->OH != a->H || a->OW != a->W ||
@@ -158,7 +167,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     if (a->view != 0 && a->view != 1) return DDM_E_BAD_ARGUMENT;
     if (a->view == 1 && a->src1 != nullptr) return DDM_E_UNSUPPORTED;
     if ((a->N_pad % 16) != 0 || a->N_pad < a->N || (a->K_pad % 64) != 0) return DDM_E_BAD_ARGUMENT;
-    if (!splitk && !a->out_f32_nchw && ((a->ld_out % 8) != 0 || !aligned16(a->out))) return DDM_E_ALIGNMENT;
+    if (!splitk && !head && !a->out_f32_nchw && ((a->ld_out % 8) != 0 || !aligned16(a->out))) return DDM_E_ALIGNMENT;
     if (a->residual != nullptr && ((a->ld_res % 8) != 0 || !aligned16(a->residual))) return DDM_E_ALIGNMENT;
     const bool shortcut = a->rsrc0 != nullptr;
     if (shortcut) {
@@ -274,6 +283,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // bf16 tiles whose channel count is a multiple of 64 leave through smem staging + TMA stores
     const bool strided_out = (a->sy != 1 || a->sx != 1);
     if (strided_out && !(a->sy == 2 && a->sx == 2 && a->OH == 2 * a->H && a->OW == 2 * a->W)) return DDM_E_UNSUPPORTED;
+    p.head_n = head ? a->head_n : 0; p.head_w = a->head_w; p.head_b = a->head_b; p.head_out = a->head_out;
     p.tma_store = (!splitk && !a->out_f32_nchw && (a->N % 64) == 0 && (!strided_out || a->ld_out == a->N) && a->OH >= a->H * a->sy &&
                    a->OW >= a->W * a->sx) ? 1 : 0;
     {   // lean epilogue kernel: staged TMA store, batch-shared scale/shift, and full tiles wherever a per-pixel side
@@ -307,6 +317,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
         }
     }
     if (shortcut && !(p.fast_epilogue && p.n_tiles == 1 && (p.block_n == 64 || p.block_n == 128))) return DDM_E_UNSUPPORTED;
+    if (head && !(p.fast_epilogue && p.fold == 0 && p.n_tiles == 1 && (p.block_n == 64 || p.block_n == 128))) return DDM_E_UNSUPPORTED;
     p.tmem_cols = pow2_ceil((shortcut ? 4 : 2) * p.block_n); if (p.tmem_cols < 32) p.tmem_cols = 32;
     p.acc_stride = p.tmem_cols / 2;
     p.acc_stages = 2;
@@ -357,8 +368,9 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     // RMSNorm + residual of the attention output (to_out), +18 % on 3x3 64->64, +35 % on C_out = 128 -- so it is used
     // for the first kind only.  DDM_CONV_DEBUG & 4194304 forces it wherever it fits, & 8388608 disables it.
     p.epi_groups = 2;
-    const bool four_groups_pays = (a->ntaps == 1 && a->norm_g != nullptr && a->residual != nullptr && p.block_n == 64) || qkv_three_tiles;
-    if (p.fast_epilogue && ((g_conv_debug & 4194304) || (four_groups_pays && !(g_conv_debug & 8388608))) && !(g_conv_debug & 2048) &&
+    // (the head lives in the two-group lean kernel)
+    const bool four_groups_pays = !head && ((a->ntaps == 1 && a->norm_g != nullptr && a->residual != nullptr && p.block_n == 64) || qkv_three_tiles);
+    if (p.fast_epilogue && !head && ((g_conv_debug & 4194304) || (four_groups_pays && !(g_conv_debug & 8388608))) && !(g_conv_debug & 2048) &&
         p.fold != 3) {
         const int cols = (p.fold ? p.fold : (shortcut ? 2 : 1)) * p.block_n;
         const int stride = pow2_ceil(cols) < 32 ? 32 : pow2_ceil(cols);
@@ -448,7 +460,7 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
             }
             return encode_bf16_map(tm, base, 5, dims, str, box);
         };
-        if (p.tma_store) {
+        if (p.tma_store && !head) {
             r = encode_out(&tmOut, a->out, a->ld_out);
             if (r != 0) return r;
         } else {
@@ -489,6 +501,12 @@ int ddm_conv2d(const ddm_conv_args* a, void* stream) {
     }
     ddm::launch_conv(tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p, g_num_sms, as_stream(stream), g_pdl);
     return finish(1);
+}
+
+int ddm_conv2d_head_supported(int N, int head_n, int H, int W) {
+    if (std::getenv("DDM_NO_FUSED_HEAD") != nullptr) return 0;
+    if ((N != 64 && N != 128) || head_n < 1 || head_n > 4 || H < 1 || W < 1) return 0;
+    return 1;
 }
 
 int ddm_conv2d_row_norm_supported(int N) {

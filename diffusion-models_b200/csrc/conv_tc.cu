@@ -55,7 +55,7 @@ __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 struct SmemPlan {
-    int a_bytes, b_chunk_bytes, stage_bytes, wres_off, staging_off, colp_off, red_off, xch_off, bars_off, total;
+    int a_bytes, b_chunk_bytes, stage_bytes, wres_off, staging_off, colp_off, head_off, red_off, xch_off, bars_off, total;
 };
 __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stages) {
     SmemPlan s;
@@ -65,7 +65,8 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
     s.wres_off = num_stages * s.stage_bytes;
     s.staging_off = s.wres_off + (p.b_resident ? (p.k_chunks + p.res_chunks) * s.b_chunk_bytes : 0);
     s.colp_off = s.staging_off + (p.tma_store ? (p.staging_bufs > 1 ? p.staging_bufs : 1) * kTileM * p.block_n * 2 : 0);
-    s.red_off = s.colp_off + (p.res_chunks ? 4 : 3) * p.n_pad * 4;
+    s.head_off = s.colp_off + (p.res_chunks ? 4 : 3) * p.n_pad * 4;     // fused head: weights [head_n][n_pad], then [2 groups][128] float4
+    s.red_off = s.head_off + (p.head_n ? p.head_n * p.n_pad * 4 + 2 * kTileM * 16 : 0);
     s.xch_off = s.red_off + (p.rnorm_out != nullptr ? 2 : 1) * kMaxParts * kTileM * 4;     // red_b only with rnorm_out
     s.bars_off = s.xch_off + (p.pair_n ? 2 * kTileM * 4 : 0);
     s.total = s.bars_off + static_cast<int>(sizeof(ConvBarriers));
@@ -75,7 +76,7 @@ __host__ __device__ inline SmemPlan make_plan(const ConvParams& p, int num_stage
 // kEpiWarps epilogue warps (multiple of 4).  FAST: lean epilogue for the common case (bf16 output through smem
 // staging + TMA store, full tiles where per-pixel side inputs are used, scale/shift shared by the batch); packed
 // f32x2 arithmetic, all per-pixel address math hoisted out of the tile loop.
-template <int kEpiWarps, bool FAST, int FOLD, int GROUPS, bool SPLITK = false>
+template <int kEpiWarps, bool FAST, int FOLD, int GROUPS, bool SPLITK = false, bool HEAD = false>
 __global__ void __launch_bounds__(96 + 32 * kEpiWarps, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
@@ -165,6 +166,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         col_mul[n] = m;
         col_add[n] = a;
         if (p.res_chunks) col_rbias[n] = (in && p.rbias != nullptr) ? __ldg(p.rbias + n) : 0.0f;
+    }
+    if constexpr (HEAD) {
+        float* hw = reinterpret_cast<float*>(smem + plan.head_off);
+        for (int i = threadIdx.x; i < p.head_n * p.n_pad; i += blockDim.x) {
+            const int o = i / p.n_pad, n = i - o * p.n_pad;
+            hw[i] = n < p.N ? __ldg(p.head_w + o * p.N + n) : 0.0f;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -484,7 +492,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t sb_rbias = smem_u32(col_rbias);
         uint32_t res_phase = 0;
         const bool want_rs = p.row_scale != nullptr, want_rn = p.rnorm_out != nullptr;
-        const bool need_geo = leader_warp || (res_smem && !res_tma) || want_rs || want_rn;   // who needs the tile's coordinates
+        const bool need_geo = leader_warp || (res_smem && !res_tma) || want_rs || want_rn || HEAD;   // who needs the tile's coordinates
         const bool skip = ((p.debug & kDbg) & 1) != 0;   // profiling: no epilogue math / stores
         const int stg_bytes = kTileM * p.block_n * 2;
         const int tiles_xy = p.tiles_x * p.tiles_y;
@@ -694,6 +702,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
 
             // ---- pass 2: normalise, scale/shift, SiLU, residual, bf16 -> staging
+            [[maybe_unused]] uint64_t hacc[4] = {0ull, 0ull, 0ull, 0ull};        // HEAD: packed partial dot products of this thread's columns
             float out_sumsq = 0.0f;
             const uint32_t my_row = smem_u32(buf) + static_cast<uint32_t>(r) * 128u;
             for (int c = c_lo; c < c_hi && !skip; ++c) {
@@ -764,6 +773,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     v[4] = fadd2(v[4], bf2_to_f2(r1.x)); v[5] = fadd2(v[5], bf2_to_f2(r1.y));
                     v[6] = fadd2(v[6], bf2_to_f2(r1.z)); v[7] = fadd2(v[7], bf2_to_f2(r1.w));
                 }
+                if constexpr (HEAD) {     // final_conv on the fp32 values: nothing is staged or stored for this tile
+                    const uint32_t ha = smem_u32(smem + plan.head_off) + static_cast<uint32_t>(nb) * 4u;
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        if (o < p.head_n) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const ulonglong2 ww = lds_128(ha + static_cast<uint32_t>(o * p.n_pad) * 4u + j * 16);
+                                hacc[o] = ffma2(v[2 * j], ww.x, hacc[o]);
+                                hacc[o] = ffma2(v[2 * j + 1], ww.y, hacc[o]);
+                            }
+                        }
+                    }
+                    continue;
+                }
                 uint32_t w[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -787,6 +811,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
             }
             if (want_rn) gred_b[part * kTileM + r] = out_sumsq;
+            [[maybe_unused]] float hsum[4];
+            if constexpr (HEAD) {          // the column parts' partial dots meet in shared memory (kGParts == 2)
+#pragma unroll
+                for (int o = 0; o < 4; ++o) { float a, b; upk2(hacc[o], a, b); hsum[o] = a + b; }
+                if (part == 1)
+                    *reinterpret_cast<float4*>(smem + plan.head_off + p.head_n * p.n_pad * 4 + (grp * kTileM + r) * 16) =
+                        make_float4(hsum[0], hsum[1], hsum[2], hsum[3]);
+            }
             fence_proxy_async();
             if (store_leader) trace_ev(tr, 3 + grp, 4, q, trn);
             {   // one barrier less per tile: the store barrier also publishes "the group's next accumulator is full"
@@ -799,7 +831,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             named_bar_sync(bar0 + 1, kGroupThreads);
             if (store_leader) trace_ev(tr, 3 + grp, 5, q, trn);
-            if (store_leader) {
+            if constexpr (HEAD) {
+                if (part == 0 && !skip && real_tile) {
+                    const float4 o1 = *reinterpret_cast<const float4*>(smem + plan.head_off + p.head_n * p.n_pad * 4 + (grp * kTileM + r) * 16);
+                    const float tot[4] = {hsum[0] + o1.x, hsum[1] + o1.y, hsum[2] + o1.z, hsum[3] + o1.w};
+                    const int x = tg.x0 + (r & (p.bw - 1)), y = tg.y0 + ((r >> p.bw_shift) & (p.bh - 1));
+                    const int b = tg.b0 + (r >> (p.bw_shift + p.bh_shift));
+                    if (x < p.W && y < p.H && b < p.B) {
+#pragma unroll
+                        for (int o = 0; o < 4; ++o)
+                            if (o < p.head_n)
+                                p.head_out[((static_cast<long long>(b) * p.head_n + o) * p.H + y) * p.W + x] = tot[o] + __ldg(p.head_b + o);
+                    }
+                }
+                // (part 1 rewrites the scratch row for the group's next tile only behind that tile's pre-norm barrier)
+            } else if (store_leader) {
                 if (!skip) {
                     const int groups = (min(p.block_n, p.N - n0) + 63) >> 6;
                     for (int g = 0; g < groups; ++g) {
@@ -1176,6 +1222,7 @@ int conv_trace_read(long long* host, int cap) {
 int conv_prepare_attributes() {
     int r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, false, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 0, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (r == 0) r = static_cast<int>(cudaFuncSetAttribute(conv_tc_kernel<16, true, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1218,6 +1265,8 @@ void launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtenso
         cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 3, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.fold == 2) {
         cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 2, 2>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
+    } else if (p.head_n) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, 0, 2, false, true>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.ksplit > 1) {
         cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, 0, 2, true>, tmA0, tmA1, tmW, tmOut, tmRes, tmR1, p);
     } else if (p.fast_epilogue) {

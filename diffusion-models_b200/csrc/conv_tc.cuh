@@ -87,6 +87,12 @@ struct ConvParams {
     int ksplit, ks_per;
     float* partial;
     long long partial_stride;
+    // fused head (its own instantiation of the lean kernel): the network's last 1x1 conv (final_conv, dd:343,390: C_out -> head_n <= 4
+    // channels, fp32 weights [head_n][N], fp32 NCHW output) applied to the fp32 values of the tile instead of storing them
+    int head_n;
+    const float* head_w;
+    const float* head_b;
+    float* head_out;
     // pair_n (generic kernel, cluster == 2): the two N tiles of one M tile run in the two CTAs of a cluster, so that a row wider
     // than one accumulator (C_out = 512) still gets its RMSNorm in the epilogue: the CTAs exchange their per-row sums of squares
     // through distributed shared memory (remote st + remote mbarrier arrive) once per tile

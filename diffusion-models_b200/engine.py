@@ -64,7 +64,8 @@ class PlanOps:
 
     def _conv(self, tag: str, pk: PackedConv, srcs: List[torch.Tensor], out: torch.Tensor, *, domain: Tuple[int, int, int],
               bias=None, row_scale=None, norm_g=None, ss=None, ss_stride=0, act=0, residual=None, out_f32_nchw=False,
-              out_map=(1, 1, 0, 0), rnorm_out=None, ld_src: Optional[List[int]] = None, into=None, shortcut=None, ksplit=None):
+              out_map=(1, 1, 0, 0), rnorm_out=None, ld_src: Optional[List[int]] = None, into=None, shortcut=None, ksplit=None,
+              head=None):
         """`shortcut` = (weight with the 1x1 shortcut appended along K, its sources, its bias): out += W_r . cat(sources) + bias."""
         wdev = self._dev(pk.weight if shortcut is None else shortcut[0])
         a = _lib.ConvArgs()
@@ -93,9 +94,14 @@ class PlanOps:
         a.act = act
         a.residual = _ptr(residual)
         a.ld_res = residual.shape[-1] if residual is not None else 0
-        a.out = out.data_ptr()
+        a.out = out.data_ptr() if out is not None else None
         a.out_f32_nchw = 1 if out_f32_nchw else 0
-        if out_f32_nchw:
+        if head is not None:            # (weight [n][N], bias [n], fp32 NCHW output): the net's last 1x1 conv rides in the epilogue
+            a.head_w, a.head_b, a.head_out, a.head_n = head[0].data_ptr(), head[1].data_ptr(), head[2].data_ptr(), head[2].shape[1]
+            a.ld_out, a.OH, a.OW = pk.n, domain[1], domain[2]
+        if head is not None:
+            pass
+        elif out_f32_nchw:
             a.ld_out = 0
             a.OH, a.OW = out.shape[2], out.shape[3]
         else:
@@ -107,7 +113,7 @@ class PlanOps:
             a.ksplit, a.partial_out = ksplit[0], ksplit[1].data_ptr()
         self._keep.append(a)
         self.op_meta[tag] = dict(M=a.B * a.H * a.W, N=a.N, K=a.K_pad, taps=a.ntaps, srcs=len(srcs),
-                                 out_bytes=a.B * a.H * a.W * a.N * (4 if out_f32_nchw else 2),
+                                 out_bytes=a.B * a.H * a.W * (a.head_n * 4 if head is not None else a.N * (4 if out_f32_nchw else 2)),
                                  in_bytes=sum(int(x.numel()) * 2 for x in srcs) + (int(residual.numel()) * 2 if residual is not None else 0))
         fn = self.lib.ddm_conv2d
         ref = C.byref(a)
@@ -238,9 +244,11 @@ class UnetEngine(PlanOps):
             x = self._resblock(st.block2, [x, skips.pop()], h, w, want_rnorm=not self._linattn_fused(st.attn, h, w))
             x = self._attention(st.attn, x, h, w)
             x, h, w = self._resample(st, x, h, w)
-        x = self._resblock(sp.final_block, [x, h0], h, w)
-        if sp.out_dim in (1, 2, 3, 4, 6, 8):      # HBM-bound head: dedicated kernel, fp32 weights, fp32 NCHW output
-            hw_, hb_ = self._f32("final_conv.weight"), self._f32("final_conv.bias")
+        hw_, hb_ = self._f32("final_conv.weight"), self._f32("final_conv.bias")
+        x = self._resblock(sp.final_block, [x, h0], h, w, head=(hw_, hb_, self.out) if sp.out_dim <= 4 else None)
+        if x is None:                             # final_conv went into final_res_block.block2's epilogue
+            pass
+        elif sp.out_dim in (1, 2, 3, 4, 6, 8):    # HBM-bound head: dedicated kernel, fp32 weights, fp32 NCHW output
             cin = x.shape[-1]
             self._add("final_conv", lambda s: lib.ddm_head_conv1x1(x.data_ptr(), hw_.data_ptr(), hb_.data_ptr(),
                                                                     self.out.data_ptr(), B, h * w, cin, sp.out_dim, s))
@@ -297,7 +305,15 @@ class UnetEngine(PlanOps):
         self._add("time.ss", lambda s: lib.ddm_small_linear(temb.data_ptr(), td, wss.data_ptr(), bss.data_ptr(),
                                                             ss_out.data_ptr(), width, rows, width, td, 1, 0, s), into)
 
-    def _block_tail(self, tag, pk, srcs, out, h, w, *, bias, g, ss, act, residual, rnorm_out=None, shortcut=None):
+    def _tail_fuses(self, pk, rows: int, shortcut) -> bool:
+        """Whether `_block_tail` runs this layer as ONE conv launch with the whole Block tail in its epilogue."""
+        c = pk.n
+        if shortcut is None and c % 8 == 0 and c <= 1024 and not os.environ.get("DDM_NO_SPLITK") and \
+                self.lib.ddm_conv2d_suggest_ksplit(rows, pk.n_pad, pk.k_pad) > 1:
+            return False
+        return c <= MAX_FUSED_NORM
+
+    def _block_tail(self, tag, pk, srcs, out, h, w, *, bias, g, ss, act, residual, rnorm_out=None, shortcut=None, head=None):
         """conv -> RMSNorm -> scale/shift -> act -> (+residual): fused into the conv epilogue when the output row
         fits one TMEM tile, otherwise conv(+bias) followed by the row-norm kernel."""
         B, lib = self.B, self.lib
@@ -310,6 +326,7 @@ class UnetEngine(PlanOps):
             # few output rows (4x4 / 8x8 levels at small per-GPU batches): K ranges of a tile on different SMs, fp32 partial sums,
             # and the Block tail over their sum in the row-norm kernel
             ws = self._splitk_workspace(ks * rows * c)
+            assert head is None
             self._conv(tag + ".splitk", pk, srcs, out, domain=(B, h, w), ksplit=(ks, ws))
             self._add(tag + ".norm", lambda s: lib.ddm_rmsnorm_act_split(ws.data_ptr(), ks, _ptr(bias), _ptr(g), _ptr(ss), self.ss_stride, h * w,
                                                                           act, _ptr(residual), out.data_ptr(), rows, c, s))
@@ -318,9 +335,9 @@ class UnetEngine(PlanOps):
             return
         if c <= MAX_FUSED_NORM:
             self._conv(tag, pk, srcs, out, domain=(B, h, w), bias=bias, norm_g=g, ss=ss, ss_stride=self.ss_stride,
-                       act=act, residual=residual, rnorm_out=rnorm_out, shortcut=shortcut)
+                       act=act, residual=residual, rnorm_out=rnorm_out, shortcut=shortcut, head=head)
             return
-        assert shortcut is None
+        assert shortcut is None and head is None
         if (g is not None and not os.environ.get("DDM_NO_PAIR_NORM") and pk.n == pk.n_pad and
                 lib.ddm_conv2d_row_norm_supported(c)):
             # 512-channel rows: the two 256-column tiles of a row in a CTA pair, RMSNorm in the epilogue (no separate norm launch)
@@ -336,8 +353,10 @@ class UnetEngine(PlanOps):
         if rnorm_out is not None:
             self._add(tag + ".rnorm", lambda s: lib.ddm_row_rnorm(out.data_ptr(), c, rnorm_out.data_ptr(), rows, c, s))
 
-    def _resblock(self, rb: ResBlockSpec, srcs: List[torch.Tensor], h: int, w: int, want_rnorm: bool = False) -> torch.Tensor:
-        """ResnetBlock.forward, dd:136-148."""
+    def _resblock(self, rb: ResBlockSpec, srcs: List[torch.Tensor], h: int, w: int, want_rnorm: bool = False,
+                  head=None) -> Optional[torch.Tensor]:
+        """ResnetBlock.forward, dd:136-148.  `head` = (weight, bias, fp32 NCHW output) of the net's final 1x1 conv: when block2 can
+        take it into its epilogue, the block's own output is never materialised and None is returned."""
         B, W_ = self.B, self._w
         split = rb.split if len(srcs) > 1 else None
         ss = self.ss[:, self.ss_offsets[rb.name]:]
@@ -362,10 +381,12 @@ class UnetEngine(PlanOps):
             res = self._act(B, h, w, rb.c_out)
             self._conv(rb.name + ".res_conv", pack_conv(W_[rb.name + ".res_conv.weight"], split), srcs, res,
                        domain=(B, h, w), bias=self._f32(rb.name + ".res_conv.bias"))
-        out = self._act(B, h, w, rb.c_out, rb.name)
+        fuse_head = (head is not None and rn is None and self._tail_fuses(pk2, B * h * w, shortcut) and
+                     self.lib.ddm_conv2d_head_supported(rb.c_out, head[2].shape[1], h, w))
+        out = None if fuse_head else self._act(B, h, w, rb.c_out, rb.name)
         self._block_tail(rb.name + ".block2", pk2, [h1], out, h, w,
                          bias=self._f32(rb.name + ".block2.proj.bias"), g=self._dev(norm_gain(W_[rb.name + ".block2.norm.g"])),
-                         ss=None, act=1, residual=res, rnorm_out=rn, shortcut=shortcut)
+                         ss=None, act=1, residual=res, rnorm_out=rn, shortcut=shortcut, head=head if fuse_head else None)
         self._last_rnorm = (out, rn)
         return out
 

@@ -98,6 +98,13 @@ typedef struct ddm_conv_args {
      * NULL / 0 and `out` is not written): ddm_rmsnorm_act_split sums the ranges and applies the Block epilogue. */
     int ksplit;
     float* partial_out;
+    /* Fused head (the network's last 1x1 conv, final_conv dd:343,390), or head_out == NULL: instead of storing the tile,
+     * head_out[b][o][y][x] = head_b[o] + sum_n head_w[o][n] * value[n] on the fp32 values the epilogue would have rounded and
+     * stored (`out` is not written and may be NULL).  head_n <= 4 outputs; see ddm_conv2d_head_supported. */
+    const float* head_w;       /* fp32 [head_n][N] (nn.Conv2d 1x1 layout)                                        */
+    const float* head_b;       /* fp32 [head_n]                                                                  */
+    float* head_out;           /* fp32 NCHW [B][head_n][H][W]                                                    */
+    int head_n;
 } ddm_conv_args;
 
 int ddm_conv2d(const ddm_conv_args* args, void* stream);
@@ -111,6 +118,8 @@ int ddm_conv2d_suggest_ksplit(long long rows, int N_pad, int K_pad);
  * one accumulator, up to 512 (multiples of 128) as two N tiles in a CTA pair exchanging sums of squares over distributed
  * shared memory (not together with rnorm_out).  Otherwise: ddm_conv2d without norm_g, then ddm_rmsnorm_act. */
 int ddm_conv2d_row_norm_supported(int N);
+/* 1 when ddm_conv2d can fuse a head of head_n outputs behind a Block-epilogue conv with N channels on H x W images. */
+int ddm_conv2d_head_supported(int N, int head_n, int H, int W);
 /* Debugging aid: with DDM_CONV_DEBUG & 128 the conv kernel records (tag, clock64) pairs from CTA 0; this drains them to
  * host memory (synchronises the device) and returns the number of pairs.  Not used by the product path. */
 int ddm_debug_conv_trace(long long* host_pairs, int cap);

@@ -100,6 +100,17 @@ class FakeLib:
         if a.scale_shift:
             rows = B if a.ss_stride else 1
             ss = self.strided_rows(a.scale_shift, rows, max(a.ss_stride, 2 * N), 2 * N, f32)
+        if a.head_out:             # fused head: the tile's fp32 values go through final_conv instead of being stored
+            res = shortcut
+            if a.residual:
+                res = self.strided_rows(a.residual, B * H * W, a.ld_res, a.ld_res, bf).float().reshape(B, H, W, a.ld_res)
+            v = torch.zeros((B, H, W, N), dtype=f32)
+            R.conv_ref(srcs, weight, N, (B, H, W), taps, view=a.view, row_scale=row_scale, bias=bias, norm_g=g, scale_shift=ss, act=a.act,
+                       residual=res, out=v, round_out=False)
+            hw = self.view(a.head_w, (a.head_n, N), f32)
+            y = v.reshape(-1, N) @ hw.t() + self.view(a.head_b, (a.head_n,), f32)
+            self.view(a.head_out, (B, a.head_n, H, W), f32).copy_(y.reshape(B, H, W, a.head_n).permute(0, 3, 1, 2))
+            return 0
         if a.out_f32_nchw:
             out = self.view(a.out, (B, N, a.OH, a.OW), f32)
             res = None
@@ -182,6 +193,9 @@ class FakeLib:
                               r.float() if r is not None else None)
         self.view(out, (rows, C_), bf).copy_(y.to(bf))
         return 0
+
+    def ddm_conv2d_head_supported(self, N, head_n, H, W):
+        return 1 if (N in (64, 128) and 1 <= head_n <= 4) else 0
 
     def ddm_conv2d_row_norm_supported(self, N):
         return 1 if (N <= 256 or (N <= 512 and N % 128 == 0)) else 0

@@ -291,6 +291,51 @@ def test_conv_row_norm_in_cta_pair(lib, B, H, W, Cin, Cout, batched):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("B,H,W,N,nh,with_sc", [(3, 32, 32, 64, 3, True), (150, 32, 32, 64, 3, True), (2, 10, 24, 64, 1, False), (3, 16, 16, 128, 4, True),
+                                                 (2, 32, 32, 64, 2, False)])
+def test_conv3x3_fused_head(lib, B, H, W, N, nh, with_sc):
+    """final_res_block.block2 + final_conv (dd:343,390): the 1x1 head applied to the tile's fp32 values in the epilogue, fp32 NCHW out;
+    with the fused shortcut (the benchmark net) or a plain residual; ragged tiles (10 x 24)."""
+    from diffusion_models_b200._lib import ConvArgs
+    from diffusion_models_b200.packing import append_shortcut, pack_conv
+    assert lib.ddm_conv2d_head_supported(N, nh, H, W) == 1
+    h1 = dev(rnd((B, H, W, N), 300), BF)
+    pk = pack_conv(rnd((N, N, 3, 3), 301, (N * 9) ** -0.5))
+    bias, g = dev(rnd((N,), 302, 0.1)), dev(1 + 0.1 * rnd((N,), 303)) * N ** 0.5
+    hw, hb = dev(rnd((nh, N), 304, N ** -0.5)), dev(rnd((nh,), 305, 0.1))
+    out = torch.full((B, nh, H, W), float("nan"), dtype=F32, device="cuda")
+    a = ConvArgs()
+    a.src0, a.C0, a.ld0 = h1.data_ptr(), N, N
+    a.B, a.H, a.W, a.ntaps = B, H, W, 9
+    for i, (dy, dx, p) in enumerate(pk.taps):
+        a.tap_dy[i], a.tap_dx[i], a.tap_p[i] = dy, dx, p
+    w = dev(pk.weight)
+    if with_sc:
+        rs = [dev(rnd((B, H, W, 64), 306 + i), BF) for i in range(2)]
+        wr, br = rnd((N, 128, 1, 1), 308, 128 ** -0.5), dev(rnd((N,), 309, 0.1))
+        w = dev(append_shortcut(pk, wr, (64, 64)))
+        a.rsrc0, a.rC0, a.rld0, a.rsrc1, a.rC1, a.rld1, a.rbias = rs[0].data_ptr(), 64, 64, rs[1].data_ptr(), 64, 64, br.data_ptr()
+        res = torch.cat([t.float() for t in rs], dim=-1) @ dev(pack_conv(wr, (64, 64)).weight).float()[:N].t() + br
+    else:
+        rt = dev(rnd((B, H, W, N), 310), BF)
+        a.residual, a.ld_res = rt.data_ptr(), N
+        res = rt.float()
+    a.weight, a.N, a.N_pad, a.K_pad = w.data_ptr(), N, pk.n_pad, w.shape[1]
+    a.bias, a.norm_g, a.act = bias.data_ptr(), g.data_ptr(), 1
+    a.ld_out, a.OH, a.OW, a.sy, a.sx = N, H, W, 1, 1
+    a.head_w, a.head_b, a.head_out, a.head_n = hw.data_ptr(), hb.data_ptr(), out.data_ptr(), nh
+    check(lib.ddm_conv2d(C.byref(a), stream()))
+    v = torch.zeros((B, H, W, N), dtype=F32, device="cuda")
+    R.conv_ref([h1.float()], dev(pk.weight).float(), N, (B, H, W), pk.taps, bias=bias, norm_g=g, act=1, residual=res, out=v, round_out=False)
+    ref = (v.reshape(-1, N) @ hw.t() + hb).reshape(B, H, W, nh).permute(0, 3, 1, 2)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    out2 = torch.zeros_like(out)
+    a.head_out = out2.data_ptr()
+    check(lib.ddm_conv2d(C.byref(a), stream()))
+    assert torch.equal(out, out2)
+
+
 def test_conv_wide_output_two_n_tiles(lib):
     """N = 384 (to_qkv, two 192-wide tiles, pre-norm row scale) and N = 512 (two 256-wide tiles)."""
     from diffusion_models_b200.packing import pack_conv
