@@ -77,6 +77,62 @@ def test_conv_issuer_modes_back_to_back():
         assert torch.isfinite(outs[0].float()).all() and torch.equal(outs[0], outs[1]), (B, H, W, Cin, Cout)
 
 
+def test_cta_pair_norm_and_split_k_back_to_back():
+    """The cluster protocol of the 512-channel Block tail (two CTAs exchanging row sums of squares through distributed shared
+    memory, double-buffered by tile parity) and the split-K instantiation: 200 launches each without a host sync, bitwise equal.
+    2400 images of 4 x 4 = 300 M tiles: every cluster walks four or five tiles; 5 images: a single, ragged tile pair."""
+    from diffusion_models_b200 import _lib
+    from diffusion_models_b200._lib import ConvArgs
+    from diffusion_models_b200.packing import pack_conv
+    lib = _lib.init(0)
+    s = torch.cuda.current_stream().cuda_stream
+    for (B, Cin, seed) in [(2400, 128, 1), (5, 512, 2)]:
+        H = W = 4
+        Cout = 512
+        x = rnd((B, H, W, Cin), 600 + seed).to("cuda", BF)
+        pk = pack_conv(rnd((Cout, Cin, 3, 3), 610 + seed, (Cin * 9) ** -0.5))
+        w = pk.weight.cuda()
+        bias, g = rnd((Cout,), 620 + seed, 0.1).cuda(), (1 + 0.1 * rnd((Cout,), 630 + seed)).cuda() * Cout ** 0.5
+        ss, res = rnd((1, 2 * Cout), 640 + seed, 0.3).cuda(), rnd((B, H, W, Cout), 650 + seed).to("cuda", BF)
+        outs = [torch.zeros((B, H, W, Cout), dtype=BF, device="cuda") for _ in range(2)]
+        a = ConvArgs()
+        a.src0, a.C0, a.ld0 = x.data_ptr(), Cin, Cin
+        a.B, a.H, a.W, a.ntaps = B, H, W, 9
+        for i, (dy, dx, p) in enumerate(pk.taps):
+            a.tap_dy[i], a.tap_dx[i], a.tap_p[i] = dy, dx, p
+        a.weight, a.N, a.N_pad, a.K_pad = w.data_ptr(), pk.n, pk.n_pad, pk.k_pad
+        a.bias, a.norm_g, a.scale_shift, a.act = bias.data_ptr(), g.data_ptr(), ss.data_ptr(), 1
+        a.residual, a.ld_res = res.data_ptr(), Cout
+        a.ld_out, a.OH, a.OW, a.sy, a.sx = Cout, H, W, 1, 1
+        a.out = outs[0].data_ptr()
+        _lib.check(lib.ddm_conv2d(C.byref(a), s))
+        a.out = outs[1].data_ptr()
+        for _ in range(200):
+            _lib.check(lib.ddm_conv2d(C.byref(a), s))
+        torch.cuda.synchronize()
+        assert torch.isfinite(outs[0].float()).all() and torch.equal(outs[0], outs[1]), (B, Cin)
+    # split-K: 16 images of 4 x 4 (two M tiles), 512 -> 512, seven K ranges
+    B, H, W, Cin, Cout, ks = 16, 4, 4, 512, 512, 7
+    x = rnd((B, H, W, Cin), 660).to("cuda", BF)
+    pk = pack_conv(rnd((Cout, Cin, 3, 3), 661, (Cin * 9) ** -0.5))
+    w = pk.weight.cuda()
+    parts = [torch.zeros((ks, B * H * W, Cout), dtype=torch.float32, device="cuda") for _ in range(2)]
+    a = ConvArgs()
+    a.src0, a.C0, a.ld0 = x.data_ptr(), Cin, Cin
+    a.B, a.H, a.W, a.ntaps = B, H, W, 9
+    for i, (dy, dx, p) in enumerate(pk.taps):
+        a.tap_dy[i], a.tap_dx[i], a.tap_p[i] = dy, dx, p
+    a.weight, a.N, a.N_pad, a.K_pad = w.data_ptr(), pk.n, pk.n_pad, pk.k_pad
+    a.ld_out, a.OH, a.OW, a.sy, a.sx = Cout, H, W, 1, 1
+    a.ksplit, a.partial_out = ks, parts[0].data_ptr()
+    _lib.check(lib.ddm_conv2d(C.byref(a), s))
+    a.partial_out = parts[1].data_ptr()
+    for _ in range(200):
+        _lib.check(lib.ddm_conv2d(C.byref(a), s))
+    torch.cuda.synchronize()
+    assert torch.isfinite(parts[0]).all() and torch.equal(parts[0], parts[1])
+
+
 def test_fused_linear_attention_and_attention_back_to_back():
     from diffusion_models_b200 import _lib
     from diffusion_models_b200._lib import LinAttnBlockArgs
