@@ -86,6 +86,8 @@ EXPORTS = {
                                     C.c_void_p]),
     "ddm_linear_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]),
+    "ddm_linear_attention_bounded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p]),
     "ddm_linear_attention_block_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ddm_linear_attention_block": (C.c_int, [C.POINTER(LinAttnBlockArgs), C.c_void_p]),
     "ddm_debug_linattn_trace": (C.c_int, [C.c_void_p, C.c_int]),

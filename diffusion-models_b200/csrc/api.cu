@@ -638,7 +638,17 @@ int ddm_linear_attention(const void* qkv_bf16, const float* mem_kv, void* out_bf
     if (!g_ready) return DDM_E_NOT_INITIALISED;
     if (!aligned16(qkv_bf16) || !aligned16(out_bf16)) return DDM_E_ALIGNMENT;
     if (B > 65535 || n_mem < 0 || n_mem > 16 || (n_mem > 0 && mem_kv == nullptr)) return DDM_E_UNSUPPORTED;
-    const int r = ddm::launch_linear_attention(qkv_bf16, mem_kv, out_bf16, B, n, heads, d, n_mem, as_stream(stream));
+    const int r = ddm::launch_linear_attention(qkv_bf16, mem_kv, nullptr, out_bf16, B, n, heads, d, n_mem, as_stream(stream));
+    return r != 0 ? r : finish(1);
+}
+
+int ddm_linear_attention_bounded(const void* qkv_bf16, const float* mem_kv, const float* k_shift, void* out_bf16, int B, int n, int heads,
+                                 int d, int n_mem, void* stream) {
+    if (!g_ready) return DDM_E_NOT_INITIALISED;
+    if (k_shift == nullptr) return DDM_E_BAD_ARGUMENT;
+    if (!aligned16(qkv_bf16) || !aligned16(out_bf16)) return DDM_E_ALIGNMENT;
+    if (d != 32 || B > 65535 || n_mem < 0 || n_mem > 16 || (n_mem > 0 && mem_kv == nullptr)) return DDM_E_UNSUPPORTED;
+    const int r = ddm::launch_linear_attention(qkv_bf16, mem_kv, k_shift, out_bf16, B, n, heads, d, n_mem, as_stream(stream));
     return r != 0 ? r : finish(1);
 }
 

@@ -265,14 +265,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat
 
 int attention_prepare_attributes() { return 0; }
 
-int launch_linear_attention(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int d, int n_mem,
-                            cudaStream_t s) {
+int launch_linear_attention(const void* qkv, const float* mem_kv, const float* k_shift, void* out, int B, int n, int heads, int d,
+                            int n_mem, cudaStream_t s) {
     const dim3 grid(heads, B);
     const auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
     auto* o = reinterpret_cast<__nv_bfloat16*>(out);
     switch (d) {
         case 16: linear_attention_kernel<16><<<grid, 256, 0, s>>>(q, mem_kv, o, n, heads, n_mem); return 0;
-        case 32: launch_linattn32_tc(qkv, mem_kv, out, B, n, heads, n_mem, s); return 0;   // tensor-core path
+        case 32: launch_linattn32_tc(qkv, mem_kv, k_shift, out, B, n, heads, n_mem, s); return 0;   // tensor-core path (the only one that takes k_shift)
         case 64: linear_attention_kernel<64><<<grid, 256, 0, s>>>(q, mem_kv, o, n, heads, n_mem); return 0;
         default: return -3;
     }

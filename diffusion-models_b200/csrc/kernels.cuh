@@ -47,7 +47,8 @@ void launch_stem_tc(const float* in0, int c0, const float* in1, int c1, const fl
                     void* out, int B, int H, int W, int Cout, int ks, int num_sms, cudaStream_t s);
 
 // linattn_tc.cu
-void launch_linattn32_tc(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int n_mem, cudaStream_t s);
+void launch_linattn32_tc(const void* qkv, const float* mem_kv, const float* k_shift, void* out, int B, int n, int heads, int n_mem,
+                         cudaStream_t s);
 
 // linattn_fused.cu (CUtensorMap-taking launcher declared in api.cu, which includes <cuda.h>)
 int linattn_fused_prepare_attributes();
@@ -55,7 +56,8 @@ bool linattn_fused_supported(int C, int n, int heads, int d, int n_mem);
 
 // attention.cu
 int attention_prepare_attributes();
-int launch_linear_attention(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int d, int n_mem, cudaStream_t s);
+int launch_linear_attention(const void* qkv, const float* mem_kv, const float* k_shift, void* out, int B, int n, int heads, int d, int n_mem,
+                            cudaStream_t s);
 int launch_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const float* mem_k, const float* mem_v,
                      int n_mem, void* out, int B, int nq, int nk, int heads, int d, cudaStream_t s);
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 __global__ void __launch_bounds__(TOK)
-linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mem_kv,
+linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mem_kv, const float* __restrict__ k_shift,
                     __nv_bfloat16* __restrict__ out, int n, int heads, int n_mem) {
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -93,8 +93,13 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     const int part = tid & 3;            // channels 8*part .. 8*part+7
     const int trow = tid >> 2;           // token within a group of 32
 
-    // ---- pass 1: per-channel max of k over the tokens (softmax over n, dd:185)
-    {
+    // ---- pass 1: per-channel max of k over the tokens (softmax over n, dd:185) -- or, when the caller supplies an upper bound of
+    // |k| per channel (pre-normalised tokens are unit vectors: |k[c]| <= ||w_c||, packing.linattn_k_shift), that bound as the
+    // shift: softmax is invariant to it, and one of the three latency-exposed passes over the tokens disappears
+    if (k_shift != nullptr) {
+        if (tid < D) kmax[tid] = __ldg(k_shift + h * D + tid);
+        __syncthreads();
+    } else {
         float mx[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) mx[c] = -INFINITY;
@@ -337,9 +342,10 @@ linattn32_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
 
 }  // namespace
 
-void launch_linattn32_tc(const void* qkv, const float* mem_kv, void* out, int B, int n, int heads, int n_mem, cudaStream_t s) {
+void launch_linattn32_tc(const void* qkv, const float* mem_kv, const float* k_shift, void* out, int B, int n, int heads, int n_mem,
+                         cudaStream_t s) {
     const dim3 grid(heads, B);
-    linattn32_tc_kernel<<<grid, TOK, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), mem_kv,
+    linattn32_tc_kernel<<<grid, TOK, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), mem_kv, k_shift,
                                              reinterpret_cast<__nv_bfloat16*>(out), n, heads, n_mem);
 }
 

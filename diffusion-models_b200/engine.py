@@ -448,8 +448,17 @@ class UnetEngine(PlanOps):
             self._conv(at.name + ".to_out", pack_conv(W_[at.name + ".to_out.weight"]), [a], out, domain=(B, h, w),
                        bias=self._f32(at.name + ".to_out.bias"), residual=x)
         else:
-            self._add(at.name + ".attend", lambda s: lib.ddm_linear_attention(
-                qkv.data_ptr(), mem.data_ptr(), a.data_ptr(), B, n, at.heads, at.dim_head, at.n_mem, s))
+            shift = None
+            if at.dim_head == 32 and not os.environ.get("DDM_NO_BOUNDED_LINATTN"):
+                sh = linattn_k_shift(W_[at.name + ".to_qkv.weight"], W_[at.name + ".norm.g"], W_[at.name + ".mem_kv"], at.heads, at.dim_head)
+                if float(sh.max()) <= MAX_K_SHIFT:          # (the bound as the softmax shift: no max pass over k, see linattn_tc.cu)
+                    shift = self._dev(sh)
+            if shift is not None:
+                self._add(at.name + ".attend", lambda s: lib.ddm_linear_attention_bounded(
+                    qkv.data_ptr(), mem.data_ptr(), shift.data_ptr(), a.data_ptr(), B, n, at.heads, at.dim_head, at.n_mem, s))
+            else:
+                self._add(at.name + ".attend", lambda s: lib.ddm_linear_attention(
+                    qkv.data_ptr(), mem.data_ptr(), a.data_ptr(), B, n, at.heads, at.dim_head, at.n_mem, s))
             out = self._act(B, h, w, c, at.name)
             self._block_tail(at.name + ".to_out", pack_conv(W_[at.name + ".to_out.0.weight"]), [a], out, h, w,
                              bias=self._f32(at.name + ".to_out.0.bias"), g=self._dev(norm_gain(W_[at.name + ".to_out.1.g"])),

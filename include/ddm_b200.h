@@ -174,6 +174,11 @@ int ddm_groupnorm_act(const void* x_bf16, const float* gamma, const float* beta,
  * ------------------------------------------------------------------------------------------------------------- */
 int ddm_linear_attention(const void* qkv_bf16, const float* mem_kv, void* out_bf16, int B, int n, int heads, int d,
                          int n_mem, void* stream);
+/* The same with a caller-supplied shift for the softmax over the tokens (d = 32 only): k_shift fp32 [heads*d] must bound
+ * k[token][channel] from above for every token (and be >= the channel's memory keys) -- e.g. ||w_c||_2 when the tokens entering
+ * to_qkv are unit vectors (the block's RMSNorm).  Saves the max pass over k; the result is the same softmax. */
+int ddm_linear_attention_bounded(const void* qkv_bf16, const float* mem_kv, const float* k_shift, void* out_bf16, int B, int n,
+                                 int heads, int d, int n_mem, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K6f: the whole LinearAttention block as ONE tcgen05 / TMA kernel (dd:173-193 plus the caller's residual dd:368,383):

@@ -243,6 +243,9 @@ class FakeLib:
         self.view(out, (B, n, heads * d), bf).copy_(y.to(bf))
         return 0
 
+    def ddm_linear_attention_bounded(self, qkv, mem_kv, k_shift, out, B, n, heads, d, n_mem, stream):
+        return self.ddm_linear_attention(qkv, mem_kv, out, B, n, heads, d, n_mem, stream)      # (the shift does not change the softmax)
+
     def ddm_linear_attention_block_supported(self, C_, n, heads, d, n_mem):
         return 1 if (C_ in (64, 128) and heads == 4 and d == 32 and n >= 128 and n % 128 == 0 and 0 <= n_mem <= 4) else 0
 

@@ -469,6 +469,20 @@ def test_linear_attention(lib, n, heads, d):
     close(out, R.linear_attention_ref(qkv.float(), mem, heads, d), 2e-2)
 
 
+@pytest.mark.parametrize("n,slack", [(64, 0.0), (64, 6.0), (1024, 2.0), (100, 0.5)])
+def test_linear_attention_bounded_shift(lib, n, slack):
+    """ddm_linear_attention_bounded: any per-channel upper bound of k (here: the true maximum + slack, also >= the memory keys) gives
+    the same softmax over the tokens as the max pass."""
+    B, heads, d = 3, 4, 32
+    qkv = dev(rnd((B, n, 3 * heads * d), 122), BF)
+    mem = dev(rnd((2, heads, d, 4), 123))
+    k = qkv.float()[:, :, heads * d:2 * heads * d]
+    shift = (torch.maximum(k.amax(dim=(0, 1)), mem[0].reshape(heads * d, -1).amax(dim=1)) + slack).contiguous()
+    out = torch.zeros((B, n, heads * d), dtype=BF, device="cuda")
+    check(lib.ddm_linear_attention_bounded(qkv.data_ptr(), mem.data_ptr(), shift.data_ptr(), out.data_ptr(), B, n, heads, d, 4, stream()))
+    close(out, R.linear_attention_ref(qkv.float(), mem, heads, d), 2e-2)
+
+
 @pytest.mark.parametrize("C_", [64, 128])
 @pytest.mark.parametrize("B,n,wscale,n_mem", [(3, 1024, 1.0, 4), (2, 128, 1.0, 4), (5, 256, 3.0, 4), (300, 256, 1.0, 4), (2, 4096, 1.0, 4),
                                               (1, 16384, 0.5, 2), (3, 384, 1.0, 0)])
